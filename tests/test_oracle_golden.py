@@ -1,0 +1,198 @@
+"""Pin the NumPy oracle against outputs of the RUNNING REFERENCE (tests/golden,
+made by oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, assert_close
+from oracle import hepmc_oracle as O
+
+G = load_golden
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3, 8, 16])
+def test_densities(ndim):
+    g = G("densities")
+    xs = g["xs_%d" % ndim]
+    for tag, bounded in (("camel", True), ("ucamel", False)):
+        assert_close(O.camel_pdf(xs, bounded=bounded), g["%s_pdf_%d" % (tag, ndim)], 1e-13, msg=tag + " pdf")
+        assert_close(O.camel_pdf_gradient(xs, bounded=bounded), g["%s_pdfgrad_%d" % (tag, ndim)], 1e-13, msg=tag + " pdfgrad")
+        assert_close(O.camel_pot(xs, bounded=bounded), g["%s_pot_%d" % (tag, ndim)], 1e-13, msg=tag + " pot")
+        with np.errstate(all="ignore"):
+            assert_close(O.camel_pot_gradient(xs, bounded=bounded), g["%s_potgrad_%d" % (tag, ndim)], 1e-12, atol=1e-12, msg=tag + " potgrad")
+    assert_close(O.gaussian_pdf(xs, 0.25, 0.7), g["gauss_pdf_%d" % ndim], 1e-13)
+    assert_close(O.gaussian_pot(xs, 0.25, 0.7), g["gauss_pot_%d" % ndim], 1e-13)
+    assert_close(O.gaussian_pot_gradient(xs, 0.25, 0.7), g["gauss_potgrad_%d" % ndim], 1e-13, atol=1e-15)
+    mu, cov = g["gaussd_mu_%d" % ndim], g["gaussd_cov_%d" % ndim]
+    assert_close(O.gaussian_pdf(xs, mu, cov), g["gaussd_pdf_%d" % ndim], 1e-13)
+    assert_close(O.gaussian_pot(xs, mu, cov), g["gaussd_pot_%d" % ndim], 1e-13)
+    assert_close(O.gaussian_pot_gradient(xs, mu, cov), g["gaussd_potgrad_%d" % ndim], 1e-13, atol=1e-15)
+    assert_close(O.uniform_pdf(xs), g["uniform_pdf_%d" % ndim], 0)
+    assert_close(O.uniform_pot(xs), g["uniform_pot_%d" % ndim], 0)
+
+
+def test_density_tail_and_banana():
+    g = G("densities")
+    assert_close(O.camel_pdf(g["xs_tail"], bounded=False), g["ucamel_pdf_tail"], 2e-13)
+    for ndim in (2, 3):
+        xs = g["banana_xs_%d" % ndim]
+        assert_close(O.banana_pdf(xs), g["banana_pdf_%d" % ndim], 1e-13)
+        assert_close(O.banana_pot(xs), g["banana_pot_%d" % ndim], 1e-13)
+    assert_close(O.banana_pot_gradient(g["banana_xs_2"]), g["banana_potgrad_2"], 1e-13)
+    assert_close(O.camel_pdf(g["xs_3"]), g["camel_call_3"], 1e-13)
+
+
+@pytest.mark.parametrize("ndim", [2, 16])
+def test_plain_mc(ndim):
+    g = G("plain_mc")
+    integral, err, f = O.plain_mc(O.camel_pdf, g["data_%d" % ndim])
+    assert_close(f, g["f_%d" % ndim], 1e-13)
+    assert_close(integral, g["integral_%d" % ndim], 1e-13)
+    assert_close(err, g["err_%d" % ndim], 1e-12)
+
+
+@pytest.mark.parametrize("tag", ["2d", "16d", "3d_vw"])
+def test_vegas(tag):
+    g = G("vegas")
+    ndim, K, c, n, iters, vw = g["params_" + tag]
+    ndim, K, n, iters = int(ndim), int(K), int(n), int(iters)
+    r = O.vegas(O.camel_pdf, ndim, K, g["idx_" + tag], g["u_" + tag], c=c,
+                var_weighted=bool(vw), chi=True)
+    assert_close(r["bounds_history"], g["bounds_" + tag], 1e-12, atol=1e-15, msg="bounds")
+    assert_close(r["integral"], g["integral_" + tag], 1e-12)
+    assert_close(r["integral_err"], g["err_" + tag], 1e-11)
+    assert_close(r["chi2"], g["chi2_" + tag], 1e-10)
+    assert_close(r["data"], g["data_" + tag], 1e-13)
+    assert_close(r["function_values"], g["f_" + tag], 1e-12)
+    assert_close(r["weights"], g["w_" + tag], 1e-12)
+
+
+def test_grid_pdf_and_importance():
+    g = G("vegas")
+    b = g["gridpdf_bounds"]
+    assert_close(O.grid_pdf(b, g["gridpdf_xs"]), g["gridpdf_pdf"], 1e-13)
+    x = O.grid_sample(b, g["imp_idx"], g["imp_u"]).T
+    assert_close(x, g["imp_data"], 1e-14)
+    w = O.grid_pdf(b, x)
+    assert_close(w, g["imp_w"], 1e-12)
+    f = O.camel_pdf(x)
+    integral, err = O.importance_mc(f, w)
+    assert_close(integral, g["imp_integral"], 1e-12)
+    assert_close(err, g["imp_err"], 1e-11)
+
+
+def test_importance_ideal_kat():
+    """reference tests/test_integration.py:44-52: exact 0.5 +- 0.0."""
+    g = G("importance_ideal")
+    integral, err = O.importance_mc(g["ys"][:, 0] if g["ys"].ndim == 2 else g["ys"], g["w"])
+    assert integral == 0.5 and err == 0.0
+
+
+@pytest.mark.parametrize("tag,e_cm,npart", [("4_100", 100., 4), ("3_50", 50., 3),
+                                            ("6_1000", 1000., 6), ("2_10", 10., 2)])
+def test_rambo(tag, e_cm, npart):
+    g = G("rambo")
+    p = O.rambo_map(g["xs_" + tag], e_cm, npart)
+    assert_close(p, g["p_" + tag], 1e-12, atol=1e-12 * e_cm)
+    assert_close(O.rambo_pdf(e_cm, npart), g["pdf_" + tag], 1e-15)
+    # physics invariants: sum p = (E,0,0,0), p^2 = 0
+    P = p.reshape(-1, npart, 4)
+    tot = P.sum(axis=1)
+    assert np.allclose(tot[:, 0], e_cm, rtol=1e-13)
+    assert np.all(np.abs(tot[:, 1:]) < 1e-12 * e_cm)
+    m2 = P[:, :, 0] ** 2 - np.sum(P[:, :, 1:] ** 2, axis=2)
+    assert np.all(np.abs(m2) < 1e-9 * e_cm ** 2)
+
+
+def test_rambo_pdf_kat():
+    assert O.rambo_pdf(100., 4) == pytest.approx(3.0961473055871514e-08, rel=1e-15)
+
+
+def test_rambo_importance():
+    g = G("rambo")
+    p = O.rambo_map(g["imp_xs"], 100., 4)
+    assert_close(p, g["imp_data"], 1e-12, atol=1e-10)
+    f = p[:, 0] * p[:, 4] / 1e3 + p[:, 3] ** 2 / 1e3
+    assert_close(f, g["imp_f"], 1e-11)
+    integral, err = O.importance_mc(f, float(g["imp_w"]))
+    assert_close(integral, g["imp_integral"], 1e-11)
+    assert_close(err, g["imp_err"], 1e-10)
+
+
+def _fill(u):
+    """NaN entries = uniforms the reference never drew (accept >= 1)."""
+    return np.where(np.isnan(u), 2.0, u)
+
+
+@pytest.mark.parametrize("tag", ["banana", "camel", "gauss"])
+def test_metropolis(tag):
+    g = G("metropolis")
+    pdf = {"banana": O.banana_pdf, "camel": O.camel_pdf,
+           "gauss": lambda x: O.gaussian_pdf(x, 0.25, 0.7)}[tag]
+    chain, acc = O.metropolis_chains(pdf, g[tag + "_x0"], g[tag + "_z"], _fill(g[tag + "_u"]),
+                                     np.sqrt(g[tag + "_cov"]))
+    assert np.array_equal(chain, g[tag + "_chain"])
+    assert np.array_equal(acc, g[tag + "_accepted"])
+
+
+def test_elm():
+    g = G("elm")
+    for tag in ("g64", "g100"):
+        c, w, q = g[tag + "_centers"], g[tag + "_widths"], g[tag + "_q"]
+        assert_close(O.elm_gauss_output_matrix(q, c, w), g[tag + "_outmat"], 1e-13)
+        assert_close(O.elm_gauss_eval(q, c, w, g[tag + "_bias"], g[tag + "_weights"]), g[tag + "_eval"], 1e-9, atol=1e-9)
+        assert_close(O.elm_gauss_eval_gradient(q, c, w, g[tag + "_weights"]), g[tag + "_grad"], 1e-9, atol=1e-7)
+    assert_close(O.elm_trig_eval(g["g64_q"], g["t48_biases"], g["t48_inweights"], g["t48_bias"], g["t48_weights"]),
+                 g["t48_eval"], 1e-9, atol=1e-6)
+    assert_close(O.elm_trig_eval_gradient(g["g64_q"], g["t48_biases"], g["t48_inweights"], g["t48_weights"]),
+                 g["t48_grad"], 1e-9, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["exact", "elm", "banana"])
+def test_hmc(tag):
+    g = G("hmc")
+    e = G("elm")
+    steps, eps, mass = g[tag + "_params"]
+    if tag == "exact":
+        pdf, grad = O.camel_pdf, O.camel_pot_gradient
+    elif tag == "elm":
+        pdf = O.camel_pdf
+        grad = lambda q: O.elm_gauss_eval_gradient(q, e["g100_centers"], e["g100_widths"], e["g100_weights"])
+    else:
+        pdf, grad = O.banana_pdf, O.banana_pot_gradient
+    chain, acc = O.hmc_chains(pdf, grad, g[tag + "_x0"], g[tag + "_p"], _fill(g[tag + "_u"]),
+                              mass, eps, int(steps))
+    assert np.array_equal(acc, g[tag + "_accepted"])
+    assert_close(chain, g[tag + "_chain"], 1e-9, atol=1e-9)
+
+
+def test_philox_kat():
+    """Random123 known-answer vectors for Philox4x32-10."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, exp in kat:
+        out = O.philox4x32(*[np.array([c], dtype=np.uint64) for c in ctr], key[0], key[1])
+        assert tuple(int(o[0]) for o in out) == exp
+
+
+def test_uniform_conventions():
+    a = np.array([0, 0xffffffff, 0x12345678], dtype=np.uint32)
+    b = np.array([0, 0xffffffff, 0x9abcdef0], dtype=np.uint32)
+    u = O.u52(a, b)
+    assert u[0] == 2.0 ** -53 and u[1] == 1.0 - 2.0 ** -53
+    assert np.all((u > 0) & (u < 1))
+    # bit-trick form used by the kernels
+    k = ((a.astype(np.uint64) >> np.uint64(12)) << np.uint64(32)) | b.astype(np.uint64)
+    trick = (k | np.uint64(0x3FF0000000000000)).view(np.float64) - (1.0 - 2.0 ** -53)
+    assert np.array_equal(trick, u)
+    for K in (1, 2, 15, 16, 50, 255):
+        bins, frac = O.vegas_bins_from_uniform(np.array([2.0 ** -53, 0.5, 1 - 2.0 ** -53]), K)
+        assert bins.max() <= K - 1 and bins.min() >= 0 and np.all((frac >= 0) & (frac < 1))
+
+
+def test_ks_restatement():
+    g = G("camel2d_reference_hist")
+    from oracle.stats_oracle import ks
+    for fam in ("cv", "hmc"):
+        assert_close(np.array(ks(g["chain_hist_" + fam], g["truth"])), g["chain_ks_" + fam], 1e-13)
