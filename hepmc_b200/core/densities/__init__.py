@@ -1,0 +1,7 @@
+from .gaussian import Gaussian
+from .camel import Camel, UnconstrainedCamel
+from .uniform import Uniform
+from .banana import Banana
+from .rambo import Rambo
+
+__all__ = ['Gaussian', 'Camel', 'UnconstrainedCamel', 'Uniform', 'Banana', 'Rambo']

@@ -1,0 +1,155 @@
+"""Separable grid on the unit hypercube: the VEGAS sampling distribution
+(hepmc/core/integration/stratified_volume.py:11-182, the parts VEGAS / ImportanceMC use).
+
+State = per axis the bin boundaries `bounds[d]` (K+1) and widths `sizes[d]` (K).  A bin is
+chosen uniformly per axis and the point uniformly inside it; pdf = 1 / (K^ndim * volume).
+The state lives in ONE device tensor `(ndim, 2K+1)` = [bounds | sizes] that the kernels
+read and `hepmc_vegas_update_grid` rewrites in place; the `bounds` / `sizes` properties
+expose it as lists of NumPy arrays like the reference.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from ..density import Distribution
+from ..util import interpret_array
+from ... import _lib, rng, config
+from . import engine
+
+
+class GridVolumes(Distribution):
+
+    def __init__(self, bounds=None, base_counts=None, default_base_count=1, ndim=1, divisions=1):
+        if base_counts:
+            raise NotImplementedError("per-bin base counts belong to StratifiedMC (out of scope)")
+        self.base_counts = dict()
+        self.default_base_count = default_base_count
+        self._grid = None       # device tensor (ndim, 2K+1), created on first device use
+        self._host = None       # float64 array (ndim, 2K+1): the authoritative copy until then
+        if bounds is None:
+            Distribution.__init__(self, ndim, False)
+            if not np.isscalar(divisions):
+                if len(divisions) != ndim:
+                    raise RuntimeError("Divisions must be scalar or of length ndim")
+                if len(set(int(k) for k in divisions)) != 1:
+                    raise NotImplementedError("hepmc_b200 grids use the same number of divisions on every axis")
+                divisions = int(divisions[0])
+            self.bounds = [np.linspace(0, 1, divisions + 1) for _ in range(ndim)]
+        else:
+            Distribution.__init__(self, len(bounds), False)
+            self.bounds = bounds
+        self.initial_bounds = [np.copy(b) for b in self.bounds]
+
+    # ---- state ------------------------------------------------------------------
+    @property
+    def divisions(self):
+        return (self._state_host().shape[1] - 1) // 2
+
+    def _state_host(self):
+        if self._grid is not None:
+            self._host = self._grid.cpu().numpy()
+        return self._host
+
+    def _set_state(self, host):
+        self._host = np.ascontiguousarray(host, dtype=np.float64)
+        self._grid = None
+        k = (self._host.shape[1] - 1) // 2
+        self.partition_count = float(k) ** self.ndim   # floating point: no int64 overflow (App. B1)
+        self.total_base_count = self.default_base_count * self.partition_count
+
+    def device_grid(self):
+        """The (ndim, 2K+1) CUDA tensor the kernels use (authoritative once created)."""
+        if self._grid is None:
+            self._grid, _ = _lib.to_device(self._host)
+        return self._grid
+
+    def reset(self):
+        self.bounds = [np.copy(b) for b in self.initial_bounds]
+
+    @property
+    def bounds(self):
+        st = self._state_host()
+        k = self.divisions
+        return [st[d, :k + 1].copy() for d in range(self.ndim)]
+
+    @bounds.setter
+    def bounds(self, bounds):
+        b = np.stack([np.asarray(x, dtype=np.float64) for x in bounds])
+        self._set_state(np.concatenate([b, np.diff(b, axis=1)], axis=1))
+
+    @property
+    def sizes(self):
+        st = self._state_host()
+        k = self.divisions
+        return [st[d, k + 1:].copy() for d in range(self.ndim)]
+
+    @sizes.setter
+    def sizes(self, sizes):
+        s = np.stack([np.asarray(x, dtype=np.float64) for x in sizes])
+        b = np.zeros((s.shape[0], s.shape[1] + 1))          # bounds[d][0] = 0 (App. B2)
+        b[:, 1:] = np.cumsum(s, axis=1)
+        self._set_state(np.concatenate([b, s], axis=1))
+
+    # ---- sampling ---------------------------------------------------------------
+    def _sample(self, count, want_idx):
+        dev = _lib.device()
+        k = self.divisions
+        x = torch.empty((self.ndim, count), dtype=torch.float64, device=dev)
+        w = torch.empty(count, dtype=torch.float64, device=dev)
+        idx = torch.empty((self.ndim, count), dtype=torch.int64, device=dev)
+        if count:
+            blk = engine.none_block(self.ndim)
+            _lib.call("hepmc_vegas_sample", ctypes.byref(blk), _lib.ptr(self.device_grid()), self.ndim, k,
+                      count, 0, _lib.default_chunk(count), rng.get_seed(), rng.next_stream(),
+                      None, None, _lib.ptr(x), None, _lib.ptr(w), _lib.ptr(idx), None, None, _lib.stream_ptr())
+        return x, w, idx
+
+    def random_bins(self, count):
+        """(ndim, count) uniformly chosen bin indices (stratified_volume.py:104-113)."""
+        return config.deliver(self._sample(int(count), True)[2])
+
+    def sample_indices(self, indices):
+        """Points uniform inside the given bins, TRANSPOSED (ndim, N) like the reference
+        (:115-122): replayed through the sampling kernel with fresh native uniforms."""
+        idx, host = _lib.to_device(indices, dtype=torch.int64)
+        n = idx.shape[1]
+        u = engine.uniform_rvs(n * self.ndim, 1).reshape(self.ndim, n).contiguous()
+        x = torch.empty((self.ndim, n), dtype=torch.float64, device=idx.device)
+        w = torch.empty(n, dtype=torch.float64, device=idx.device)
+        io = torch.empty((self.ndim, n), dtype=torch.int64, device=idx.device)
+        if n:
+            blk = engine.none_block(self.ndim)
+            _lib.call("hepmc_vegas_sample", ctypes.byref(blk), _lib.ptr(self.device_grid()), self.ndim,
+                      self.divisions, n, 0, _lib.default_chunk(n), 0, 0, _lib.ptr(idx), _lib.ptr(u),
+                      _lib.ptr(x), None, _lib.ptr(w), _lib.ptr(io), None, None, _lib.stream_ptr())
+        return _lib.to_host_like(x, host)
+
+    def rvs(self, sample_count):
+        """(N, ndim) points distributed like the grid (:124-126)."""
+        x, _, _ = self._sample(int(sample_count), False)
+        return config.deliver(x.t().contiguous())
+
+    # ---- density ----------------------------------------------------------------
+    def pdf_indices(self, indices):
+        idx = torch.as_tensor(np.asarray(indices) if not isinstance(indices, torch.Tensor) else indices)
+        st = torch.as_tensor(self._state_host())
+        k = self.divisions
+        vols = torch.ones(idx.shape[1], dtype=torch.float64)
+        for d in range(self.ndim):
+            vols = vols * st[d, k + 1:][idx[d].cpu().long()]
+        out = self.default_base_count / self.total_base_count / vols
+        return out.numpy()
+
+    def pdf(self, xs):
+        """1 / (K^ndim * bin volume) inside the open unit cube, 0 outside (:74-83)."""
+        xs = interpret_array(xs, self.ndim)
+        x_dev, host = _lib.to_device(xs)
+        out = torch.empty(x_dev.shape[0], dtype=torch.float64, device=x_dev.device)
+        if x_dev.shape[0]:
+            _lib.call("hepmc_grid_pdf", _lib.ptr(self.device_grid()), self.ndim, self.divisions, _lib.ptr(x_dev),
+                      x_dev.shape[0], _lib.ptr(out), _lib.stream_ptr())
+        return _lib.to_host_like(out, host)
+
+    def pdf_gradient(self, xs):
+        raise NotImplementedError("Density is a step function.")

@@ -1,0 +1,62 @@
+"""Metropolis updates (mirror of hepmc/core/markov/metropolis.py:20-127).
+
+`DefaultMetropolis(ndim, target, proposal=None)`: accept with min(1, pdf(cand)/pdf(state)).
+Device kernel: target = a built-in density (or its bound `pdf`), proposal =
+`proposals.Gaussian` with a diagonal covariance (random walk) or the reference's default
+`densities.Uniform` independence proposal.
+"""
+import numpy as np
+
+from ..density import Density, as_builtin
+from ..densities import Uniform
+from .base import MarkovUpdate
+from . import ensemble
+
+
+class MetropolisUpdate(MarkovUpdate):
+
+    def __init__(self, ndim, target, adaptive=False, hasting=False):
+        super().__init__(ndim, is_adaptive=adaptive, target=target)
+        self.pdf = target.pdf if isinstance(target, Density) else target
+        self.is_hasting = hasting
+
+    def proposal_pdf(self, state, candidate):
+        pass
+
+
+class DefaultMetropolis(MetropolisUpdate):
+
+    def __init__(self, ndim, target, proposal=None, adaptive=False):
+        if proposal is None:
+            proposal = Uniform(ndim)
+        self._proposal = proposal
+        super().__init__(ndim, target, adaptive=adaptive, hasting=not proposal.is_symmetric)
+
+    def proposal_pdf(self, state, candidate):
+        return self._proposal.proposal_pdf(state, candidate)
+
+    def _proposal_params(self):
+        from ..proposals import Gaussian as GaussianProposal
+        prop = self._proposal
+        if isinstance(prop, GaussianProposal):
+            cov = np.asarray(prop.cov)
+            if np.count_nonzero(cov - np.diag(np.diagonal(cov))):
+                raise TypeError("the RWM kernel supports diagonal proposal covariances")
+            return 0, np.sqrt(np.diagonal(cov))
+        if isinstance(prop, Uniform):
+            return 1, np.array([prop.low, prop.high], dtype=np.float64)
+        raise TypeError("DefaultMetropolis on the device needs proposals.Gaussian or densities.Uniform, got "
+                        + type(prop).__name__)
+
+    def _run_ensemble(self, x0, sample_size, thin, store_chain, first_chain, replay):
+        dens = as_builtin(self.target) or as_builtin(self.pdf)
+        if dens is None:
+            raise TypeError("DefaultMetropolis on the device needs a built-in target density (Camel, "
+                            "UnconstrainedCamel, Banana, Gaussian, Uniform); there is no CPU fallback.")
+        if dens.ndim != self.ndim:
+            raise ValueError('target must have dimension ' + str(self.ndim))
+        if self.is_adaptive:
+            raise TypeError("adaptive Metropolis mutates shared state per step: out of scope")
+        kind, params = self._proposal_params()
+        return ensemble.run_rwm(dens._block(), x0, kind, params, sample_size, thin, store_chain,
+                                first_chain, None, replay)

@@ -1,0 +1,106 @@
+"""Result containers (mirror of hepmc/core/sampling.py:23-145, host-side and thin).
+
+`data`, `weights`, `function_values` may be NumPy arrays or CUDA tensors; the lazy
+summaries are computed with whichever library holds the data.  The O(N^2)
+autocovariance-based statistics of the reference (effective sample size, bin-wise chi^2)
+are post-hoc host analysis and are not part of the accelerated path.
+"""
+import json
+import os
+import time
+
+import numpy as np
+import torch
+
+
+def _set(*args):
+    return all(arg is not None for arg in args)
+
+
+def _concat(a, b):
+    if isinstance(a, torch.Tensor):
+        return torch.cat((a, b), dim=0)
+    return np.concatenate((a, b), axis=0)
+
+
+class Sample(object):
+    def __init__(self, **kwargs):
+        self.data = None
+        self.target = None
+        self.weights = None
+        self._variance = None
+        self._mean = None
+        self._sample_info = [
+            ('size', 'data (size)', '%s'),
+            ('mean', 'mean', '%s'),
+            ('variance', 'variance', '%s'),
+        ]
+        for key in kwargs:
+            setattr(self, key, kwargs[key])
+
+    def extend_array(self, key, array):
+        current = getattr(self, key)
+        setattr(self, key, array if current is None else _concat(current, array))
+
+    @property
+    def size(self):
+        try:
+            return self.data.shape[0]
+        except AttributeError:
+            return None
+
+    @property
+    def ndim(self):
+        try:
+            return self.data.shape[1]
+        except AttributeError:
+            return None
+
+    @property
+    def mean(self):
+        if self._mean is None and _set(self.data):
+            d = self.data
+            self._mean = d.mean(dim=0) if isinstance(d, torch.Tensor) else np.mean(d, axis=0)
+        return self._mean
+
+    @property
+    def variance(self):
+        if self._variance is None and _set(self.data):
+            d = self.data
+            self._variance = d.var(dim=0, unbiased=False) if isinstance(d, torch.Tensor) else np.var(d, axis=0)
+        return self._variance
+
+    @property
+    def effective_sample_size(self):
+        return None
+
+    @property
+    def bin_wise_chi2(self):
+        return None
+
+    def save(self, file_path=None):
+        if file_path is None:
+            file_path = type(self).__name__ + '-' + str(int(time.time()))
+        path, name = os.path.split(file_path)
+        info = {entry[0]: repr(getattr(self, entry[0])) for entry in self._sample_info}
+        info['type'] = type(self).__name__
+        info['target'] = repr(self.target)
+        data = self.data.cpu().numpy() if isinstance(self.data, torch.Tensor) else self.data
+        np.save(os.path.join(path, name + '-data.npy'), data)
+        with open(os.path.join(path, name + '.json'), 'w') as fp:
+            json.dump(info, fp, indent=2)
+
+    def _data_table(self):
+        titles = [entry[1] for entry in self._sample_info]
+        entries = []
+        for entry in self._sample_info:
+            value = getattr(self, entry[0])
+            try:
+                entries.append(entry[2] % value)
+            except TypeError:
+                entries.append('N/A')
+        return titles, entries
+
+    def __repr__(self):
+        return (type(self).__name__ + '\n\t' + '\n\t'.join(
+            '%s: %s' % (t, e) for t, e in zip(*self._data_table())))

@@ -1,0 +1,5 @@
+from .helper import (assure_2d, interpret_array, damped_update, hypercube_bounded,
+                     Counted, count_calls, host_function)
+
+__all__ = ['assure_2d', 'interpret_array', 'damped_update', 'hypercube_bounded',
+           'Counted', 'count_calls', 'host_function']

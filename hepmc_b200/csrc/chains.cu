@@ -1,0 +1,355 @@
+// Ensembles of independent Markov chains, one chain per thread, whole trajectory in-kernel:
+//   * random-walk Metropolis with a diagonal Gaussian proposal (rwm_kernel)
+//   * Hamiltonian Monte Carlo, leapfrog with un-merged half steps, exact or ELM-surrogate
+//     gradient, Metropolis test on  pdf(q) * N(p)  (hmc_kernel)
+// State (x, pdf, counters) lives in registers; randomness is Philox4x32-10 keyed by the
+// GLOBAL chain index and the step, so any split of the chain range over GPUs reproduces
+// the same chains.  Acceptance counts: per chain + warp-shuffle reduced grid total.
+#include "density.cuh"
+#include "elm.cuh"
+
+namespace hepmc {
+
+struct ChainArgs {
+    const double* x0;
+    int64_t n_chains, first_chain, T, thin, n_kept;
+    uint64_t seed;
+    uint32_t stream_id;
+    const double* z_replay;  // rwm: normals (C, T-1, nd); hmc: momenta (C, T-1, nd)
+    const double* u_replay;  // (C, T-1)
+    double* chain;           // (C, n_kept, nd) or NULL
+    double* last;            // (C, nd)
+    int64_t* accepted;       // (C,)
+    unsigned long long* total_accepted;
+    double scale[HEPMC_MAX_CHAIN_DIM];  // rwm: sqrt(diag cov); hmc: sqrt(mass)
+    int prop_kind;                      // rwm: 0 = Gaussian random walk, 1 = uniform independence on (lo, hi)
+    double prop_lo, prop_hi;
+    // hmc
+    double step_size;
+    int steps;
+    int precision;
+};
+
+// two standard normals from one Philox call (Box-Muller on two 52-bit uniforms)
+__device__ __forceinline__ void normal_pair(const U4& r, double& z0, double& z1) {
+    const double u1 = u52(r.x, r.y), u2 = u52(r.z, r.w);
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    z0 = rad * cs;
+    z1 = rad * sn;
+}
+
+template <int NDIM>
+__device__ __forceinline__ void store_state(double* chain, int64_t c, int64_t n_kept, int64_t slot,
+                                            const double (&x)[NDIM]) {
+    double* o = chain + ((size_t)c * n_kept + slot) * NDIM;
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) o[d] = x[d];
+}
+
+__device__ __forceinline__ void finish_counts(const ChainArgs& a, bool active, int64_t c, int64_t acc) {
+    if (active && a.accepted) a.accepted[c] = acc;
+    const int64_t tot = warp_sum_i64(active ? acc : 0);
+    if ((threadIdx.x & 31) == 0 && a.total_accepted && tot) atomicAdd(a.total_accepted, (unsigned long long)tot);
+}
+
+// ------------------------------------------------------------------ random-walk Metropolis
+// base.py:56-97, metropolis.py:76-95,122-124, proposals/gaussian.py:25-27
+template <int NDIM>
+__global__ void __launch_bounds__(128) rwm_kernel(const __grid_constant__ Dens dens,
+                                                  const __grid_constant__ ChainArgs a) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = c < a.n_chains;
+    const PhiloxKey key = philox_expand(a.seed);
+    constexpr int NCALL = (NDIM + 1) / 2;  // Philox calls for the proposal normals
+    constexpr uint32_t CPS = NCALL + 1;    // + one for the accept uniform
+    int64_t acc = 0;
+    if (active) {
+        const uint64_t g = (uint64_t)(a.first_chain + c);
+        double x[NDIM];
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) x[d] = a.x0[c * NDIM + d];
+        double pdf = density_pdf_n<NDIM>(dens, x);  // init_state, metropolis.py:68-74
+        if (a.chain) store_state<NDIM>(a.chain, c, a.n_kept, 0, x);
+        for (int64_t t = 1; t < a.T; ++t) {
+            double cand[NDIM];
+            double z[NDIM];  // standard normals (random walk) or uniforms (independence proposal)
+            if (a.z_replay) {
+                const double* zt = a.z_replay + ((size_t)c * (a.T - 1) + (t - 1)) * NDIM;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) z[d] = zt[d];
+            } else {
+#pragma unroll
+                for (int k = 0; k < NCALL; ++k) {
+                    const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(t - 1) * CPS + k,
+                                               a.stream_id, key);
+                    double z0, z1;
+                    if (a.prop_kind == 0) {
+                        normal_pair(r, z0, z1);
+                    } else {
+                        z0 = u52(r.x, r.y);
+                        z1 = u52(r.z, r.w);
+                    }
+                    z[2 * k] = z0;
+                    if (2 * k + 1 < NDIM) z[(2 * k + 1) % NDIM] = z1;
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d)
+                cand[d] = a.prop_kind == 0 ? x[d] + a.scale[d] * z[d]            // proposals/gaussian.py:25-27
+                                           : a.prop_lo + (a.prop_hi - a.prop_lo) * z[d];  // uniform.py:33-34
+            const double cpdf = density_pdf_n<NDIM>(dens, cand);
+            const double ratio = cpdf / pdf;  // metropolis.py:50
+            double u;
+            if (a.u_replay) {
+                u = a.u_replay[(size_t)c * (a.T - 1) + (t - 1)];
+            } else {
+                const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(t - 1) * CPS + NCALL,
+                                           a.stream_id, key);
+                u = u52(r.x, r.y);
+            }
+            if (ratio >= 1.0 || u < ratio) {  // metropolis.py:87 (NaN -> reject)
+                bool changed = false;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) {
+                    changed = changed || (cand[d] != x[d]);
+                    x[d] = cand[d];
+                }
+                pdf = cpdf;
+                acc += changed ? 1 : 0;  // base.py:72-73
+            }
+            if (a.chain && (t % a.thin) == 0) store_state<NDIM>(a.chain, c, a.n_kept, t / a.thin, x);
+        }
+        if (a.last) {
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) a.last[c * NDIM + d] = x[d];
+        }
+    }
+    finish_counts(a, active, c, acc);
+}
+
+// ------------------------------------------------------------------ HMC
+// hmc.py:54-88, simulation.py:34-42.  pdist = Gaussian(0, diag(mass)) as a Dens block.
+template <int NDIM, class T>
+__global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ Dens dens,
+                                                  const __grid_constant__ Dens pdist,
+                                                  const __grid_constant__ hepmc_elm_t elm,
+                                                  const __grid_constant__ ChainArgs a, int tab_in_smem) {
+    extern __shared__ double smem_raw[];
+    T* tab = reinterpret_cast<T*>(smem_raw);
+    const bool use_elm = elm.mode != HEPMC_GRAD_EXACT;
+    if (use_elm && tab_in_smem) {
+        elm_stage_tables<T>(elm, NDIM, tab);
+        __syncthreads();
+    }
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = c < a.n_chains;
+    const PhiloxKey key = philox_expand(a.seed);
+    constexpr int NCALL = (NDIM + 1) / 2;
+    constexpr uint32_t CPS = NCALL + 1;
+    const double half_eps = a.step_size / 2;
+    int64_t acc = 0;
+    if (active) {
+        const uint64_t g = (uint64_t)(a.first_chain + c);
+        double x[NDIM];
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) x[d] = a.x0[c * NDIM + d];
+        double pdf = density_pdf_n<NDIM>(dens, x);
+        if (a.chain) store_state<NDIM>(a.chain, c, a.n_kept, 0, x);
+        for (int64_t t = 1; t < a.T; ++t) {
+            double p0[NDIM], q[NDIM], p[NDIM], grad[NDIM];
+            if (a.z_replay) {
+                const double* z = a.z_replay + ((size_t)c * (a.T - 1) + (t - 1)) * NDIM;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) p0[d] = z[d];
+            } else {
+#pragma unroll
+                for (int k = 0; k < NCALL; ++k) {
+                    const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(t - 1) * CPS + k,
+                                               a.stream_id, key);
+                    double z0, z1;
+                    normal_pair(r, z0, z1);
+                    p0[2 * k] = a.scale[2 * k] * z0;  // gaussian.py:49-51 with mean 0
+                    if (2 * k + 1 < NDIM) p0[(2 * k + 1) % NDIM] = a.scale[(2 * k + 1) % NDIM] * z1;
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) { q[d] = x[d]; p[d] = p0[d]; }
+            // leapfrog, simulation.py:36-42
+            if (use_elm) elm_gradient<NDIM, T>(elm.mode, elm.nodes, tab, q, grad);
+            else density_pot_gradient_n<NDIM>(dens, q, grad);
+            for (int s = 0; s < a.steps; ++s) {
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) q[d] += a.step_size * (pdist.c[d] * (p[d] - pdist.a[d]));
+                if (use_elm) elm_gradient<NDIM, T>(elm.mode, elm.nodes, tab, q, grad);
+                else density_pot_gradient_n<NDIM>(dens, q, grad);
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
+            }
+            const double cpdf = density_pdf_n<NDIM>(dens, q);              // hmc.py:80
+            const double np1 = density_pdf_n<NDIM>(pdist, p);
+            const double np0 = density_pdf_n<NDIM>(pdist, p0);
+            double prob = cpdf * np1 / pdf / np0;                          // hmc.py:56-57
+            if (isnan(prob)) prob = 0.0;                                   // hmc.py:58-59
+            double u;
+            if (a.u_replay) {
+                u = a.u_replay[(size_t)c * (a.T - 1) + (t - 1)];
+            } else {
+                const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(t - 1) * CPS + NCALL,
+                                           a.stream_id, key);
+                u = u52(r.x, r.y);
+            }
+            if (prob >= 1.0 || u < prob) {
+                bool changed = false;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) {
+                    changed = changed || (q[d] != x[d]);
+                    x[d] = q[d];
+                }
+                pdf = cpdf;
+                acc += changed ? 1 : 0;
+            }
+            if (a.chain && (t % a.thin) == 0) store_state<NDIM>(a.chain, c, a.n_kept, t / a.thin, x);
+        }
+        if (a.last) {
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) a.last[c * NDIM + d] = x[d];
+        }
+    }
+    finish_counts(a, active, c, acc);
+}
+
+static int fill_chain_args(ChainArgs& a, const char* who, int ndim, const double* x0_dev, const double* scale_host,
+                           int scale_len, bool sqrt_scale, int64_t n_chains, int64_t first_chain, int64_t sample_size, int64_t thin,
+                           uint64_t seed, uint32_t stream_id, const double* z, const double* u, double* chain_dev,
+                           double* last_dev, int64_t* accepted_dev, int64_t* total_dev) {
+    HEPMC_REQUIRE(ndim >= 1 && ndim <= HEPMC_MAX_CHAIN_DIM, HEPMC_E_UNSUPPORTED, "%s: ndim %d outside [1,%d]", who, ndim,
+                  HEPMC_MAX_CHAIN_DIM);
+    HEPMC_REQUIRE(n_chains >= 0 && first_chain >= 0 && sample_size >= 1 && thin >= 1, HEPMC_E_ARG,
+                  "%s: bad n_chains/sample_size/thin", who);
+    HEPMC_REQUIRE(sample_size < ((int64_t)1 << 28), HEPMC_E_UNSUPPORTED, "%s: sample_size too large for the counter layout", who);
+    HEPMC_REQUIRE(x0_dev && scale_host, HEPMC_E_ARG, "%s: NULL x0/scale", who);
+    HEPMC_REQUIRE((z == nullptr) == (u == nullptr), HEPMC_E_ARG, "%s: replay needs both tapes", who);
+    a.x0 = x0_dev; a.n_chains = n_chains; a.first_chain = first_chain; a.T = sample_size; a.thin = thin;
+    a.n_kept = (sample_size + thin - 1) / thin;
+    a.seed = seed; a.stream_id = stream_id; a.z_replay = z; a.u_replay = u;
+    a.chain = chain_dev; a.last = last_dev; a.accepted = accepted_dev;
+    a.total_accepted = reinterpret_cast<unsigned long long*>(total_dev);
+    for (int d = 0; d < HEPMC_MAX_CHAIN_DIM; ++d) a.scale[d] = 0.0;
+    if (scale_len > ndim) scale_len = ndim;
+    for (int d = 0; d < scale_len; ++d) a.scale[d] = sqrt_scale ? sqrt(scale_host[d]) : scale_host[d];
+    return 0;
+}
+
+}  // namespace hepmc
+
+using namespace hepmc;
+
+extern "C" {
+
+int hepmc_rwm_chains(const hepmc_density_t* dens, const double* x0_dev, int proposal_kind,
+                     const double* prop_scale_host, int64_t n_chains, int64_t first_chain, int64_t sample_size, int64_t thin,
+                     uint64_t seed, uint32_t stream_id,
+                     const double* z_replay_dev, const double* u_replay_dev,
+                     double* chain_dev, double* last_dev, int64_t* accepted_dev,
+                     int64_t* total_accepted_dev, void* stream) {
+    HEPMC_REQUIRE(dens != nullptr, HEPMC_E_ARG, "hepmc_rwm_chains: dens is NULL");
+    HEPMC_REQUIRE(dens->kind >= HEPMC_CAMEL && dens->kind <= HEPMC_UNIFORM, HEPMC_E_ARG,
+                  "hepmc_rwm_chains: target must be a built-in density (kind %d)", dens->kind);
+    ChainArgs a{};
+    int e = fill_chain_args(a, "hepmc_rwm_chains", dens->ndim, x0_dev, prop_scale_host,
+                            proposal_kind == 1 ? 0 : dens->ndim, false, n_chains, first_chain,
+                            sample_size, thin, seed, stream_id, z_replay_dev, u_replay_dev, chain_dev, last_dev,
+                            accepted_dev, total_accepted_dev);
+    if (e) return e;
+    HEPMC_REQUIRE(proposal_kind == 0 || proposal_kind == 1, HEPMC_E_ARG, "hepmc_rwm_chains: proposal_kind must be 0 or 1");
+    a.prop_kind = proposal_kind;
+    if (proposal_kind == 1) {
+        a.prop_lo = prop_scale_host[0];
+        a.prop_hi = prop_scale_host[1];
+    }
+    if (n_chains == 0) return 0;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((n_chains + threads - 1) / threads);
+    cudaStream_t st = as_stream(stream);
+#define RWM_CASE(ND) rwm_kernel<ND><<<blocks, threads, 0, st>>>(*dens, a)
+    HEPMC_DISPATCH_NDIM(dens->ndim, RWM_CASE);
+#undef RWM_CASE
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int precision,
+                     const double* x0_dev, const double* mass_host, double step_size, int steps,
+                     int64_t n_chains, int64_t first_chain, int64_t sample_size, int64_t thin,
+                     uint64_t seed, uint32_t stream_id,
+                     const double* p_replay_dev, const double* u_replay_dev,
+                     double* chain_dev, double* last_dev, int64_t* accepted_dev,
+                     int64_t* total_accepted_dev, void* stream) {
+    HEPMC_REQUIRE(dens != nullptr, HEPMC_E_ARG, "hepmc_hmc_chains: dens is NULL");
+    HEPMC_REQUIRE(dens->kind >= HEPMC_CAMEL && dens->kind <= HEPMC_UNIFORM, HEPMC_E_ARG,
+                  "hepmc_hmc_chains: target must be a built-in density (kind %d)", dens->kind);
+    HEPMC_REQUIRE(steps >= 0, HEPMC_E_ARG, "hepmc_hmc_chains: steps < 0");
+    HEPMC_REQUIRE(precision >= 0 && precision <= 2, HEPMC_E_ARG, "hepmc_hmc_chains: precision must be 0, 1 or 2");
+    HEPMC_REQUIRE(precision != 2, HEPMC_E_UNSUPPORTED,
+                  "hepmc_hmc_chains: tensor-core surrogate (precision 2) is served by hepmc_hmc_chains_tc");
+    const int nd = dens->ndim;
+    ChainArgs a{};
+    int e = fill_chain_args(a, "hepmc_hmc_chains", nd, x0_dev, mass_host, nd, true, n_chains, first_chain, sample_size, thin,
+                            seed, stream_id, p_replay_dev, u_replay_dev, chain_dev, last_dev, accepted_dev,
+                            total_accepted_dev);
+    if (e) return e;
+    a.step_size = step_size; a.steps = steps; a.precision = precision;
+    hepmc_elm_t el{};
+    el.mode = HEPMC_GRAD_EXACT;
+    if (elm != nullptr && elm->mode != HEPMC_GRAD_EXACT) {
+        HEPMC_REQUIRE(elm->mode == HEPMC_GRAD_ELM_GAUSS || elm->mode == HEPMC_GRAD_ELM_TRIG, HEPMC_E_ARG,
+                      "hepmc_hmc_chains: bad surrogate mode %d", elm->mode);
+        HEPMC_REQUIRE(elm->nodes >= 1 && elm->p0_dev && elm->p1_dev && elm->out_w_dev, HEPMC_E_ARG,
+                      "hepmc_hmc_chains: incomplete surrogate parameters");
+        el = *elm;
+    } else {
+        HEPMC_REQUIRE(!(dens->kind == HEPMC_BANANA && nd != 2), HEPMC_E_UNSUPPORTED,
+                      "Banana.pot_gradient exists for ndim == 2 only (banana.py:44-51)");
+    }
+    // momentum distribution Gaussian(0, diag(mass)): gaussian.py:30-51,73-76
+    Dens pd{};
+    pd.kind = HEPMC_GAUSSIAN; pd.ndim = nd;
+    double logdet = 0.0;
+    for (int d = 0; d < nd; ++d) {
+        HEPMC_REQUIRE(mass_host[d] > 0.0, HEPMC_E_ARG, "hepmc_hmc_chains: mass must be positive");
+        pd.a[d] = 0.0; pd.b[d] = sqrt(1.0 / mass_host[d]); pd.c[d] = 1.0 / mass_host[d];
+        logdet += log(mass_host[d]);
+    }
+    pd.s1 = nd * log(2.0 * 3.141592653589793) + logdet;
+    if (n_chains == 0) return 0;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((n_chains + threads - 1) / threads);
+    cudaStream_t st = as_stream(stream);
+    int dev = 0, maxs = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&maxs, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const size_t esz = precision == 0 ? 8 : 4;
+    size_t smem = el.mode == HEPMC_GRAD_EXACT ? 0 : (size_t)el.nodes * elm_row(nd) * esz;
+    HEPMC_REQUIRE(smem <= (size_t)maxs, HEPMC_E_UNSUPPORTED,
+                  "hepmc_hmc_chains: %d surrogate nodes do not fit shared memory (%zu > %d bytes)", el.nodes, smem, maxs);
+#define HMC_CASE(ND)                                                                                       \
+    do {                                                                                                   \
+        if (precision == 0) {                                                                              \
+            HEPMC_CUDA(cudaFuncSetAttribute(hmc_kernel<ND, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            hmc_kernel<ND, double><<<blocks, threads, smem, st>>>(*dens, pd, el, a, 1);                    \
+        } else {                                                                                           \
+            HEPMC_CUDA(cudaFuncSetAttribute(hmc_kernel<ND, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+            hmc_kernel<ND, float><<<blocks, threads, smem, st>>>(*dens, pd, el, a, 1);                     \
+        }                                                                                                  \
+    } while (0)
+    HEPMC_DISPATCH_NDIM(nd, HMC_CASE);
+#undef HMC_CASE
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

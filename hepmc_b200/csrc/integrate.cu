@@ -1,0 +1,704 @@
+// Plain MC and VEGAS importance-sampling integration, fused: Philox draw -> grid map ->
+// integrand -> weight -> per-thread shifted moments + per-(axis,bin) histogram.
+//
+// Determinism / GPU-count invariance: the global point range of one iteration is cut into
+// fixed CHUNKS (one CTA each, fixed point->thread->order mapping); every chunk writes one
+// partial row (count, mean, M2 | hist[ndim*K]); partial rows are merged in chunk order by
+// the reduce kernels.  No floating-point atomics anywhere, so results are bit-identical for
+// any partition of the chunk range over GPUs.
+//
+// Histogram without atomics: after each warp-tile of 32 points the lanes swap roles -- lane
+// L owns axis d = L % ndim and a PRIVATE column hist[k][L] in shared memory, and walks the
+// tile's points in fixed order (plain LDS/DADD/STS, conflict-free banks).  The per-lane
+// columns are summed in fixed order when the chunk ends.
+#include "density.cuh"
+
+namespace hepmc {
+
+constexpr int kBinWords = HEPMC_MAX_DIM / 4 + 1;  // packed bin bytes per point, padded (bank-conflict-free)
+
+struct SampleArgs {
+    const double* grid;  // VEGAS: (ndim, 2K+1); plain: unused
+    int ndim, K;
+    int64_t n, first_index, chunk;
+    uint64_t seed;
+    uint32_t stream_id;
+    const int64_t* idx_replay;
+    const double* u_replay;
+    double* x_out;
+    double* f_out;
+    double* w_out;
+    int64_t* idx_out;
+    double* stats_partials;
+    double* hist_partials;
+    double kpow;
+    // two-kernel path inputs (accumulate)
+    const double* f_in;
+    const double* w_in;
+    const int64_t* idx_in;
+};
+
+// lane L < ngrp*ndim: axis d = L % ndim, walks points grp, grp+ngrp, ... of the warp tile.
+__device__ __forceinline__ void warp_hist_update(double* hist_w, const double* wf_w, const uint32_t* bins_w,
+                                                 int ndim, int lane) {
+    const int ngrp = 32 / ndim;
+    if (lane < ngrp * ndim) {
+        const int d = lane % ndim, grp = lane / ndim;
+        const int word = d >> 2, shift = 8 * (d & 3);
+        for (int p = grp; p < 32; p += ngrp) {
+            const double v = wf_w[p];
+            const uint32_t bin = (bins_w[p * kBinWords + word] >> shift) & 0xffu;
+            hist_w[bin * 32 + lane] += v;
+        }
+    }
+}
+
+__device__ __forceinline__ void block_hist_flush(const double* s_hist, int ndim, int K, int nwarps,
+                                                 double* out_row) {
+    const int ngrp = 32 / ndim;
+    for (int j = threadIdx.x; j < ndim * K; j += blockDim.x) {
+        const int d = j / K, k = j % K;
+        double s = 0.0;
+        for (int w = 0; w < nwarps; ++w)
+            for (int g = 0; g < ngrp; ++g) s += s_hist[(w * K + k) * 32 + g * ndim + d];
+        out_row[j] = s;
+    }
+}
+
+struct SmemLayout {
+    double* grid;
+    Stats* stats;
+    double* hist;
+    double* wf;
+    uint32_t* bins;
+};
+
+__host__ __device__ inline size_t vegas_smem_bytes(int ndim, int K, int threads) {
+    const int nw = threads / 32;
+    size_t b = (size_t)ndim * (2 * K + 1) * 8;  // grid
+    b += 32 * sizeof(Stats);                    // block merge scratch
+    b += (size_t)nw * K * 32 * 8;               // private histogram columns
+    b += (size_t)nw * 32 * 8;                   // wf tile
+    b += (size_t)nw * 32 * kBinWords * 4;       // packed bins tile
+    return b;
+}
+
+__device__ __forceinline__ SmemLayout carve(double* base, int ndim, int K, int nw) {
+    SmemLayout s;
+    s.grid = base;
+    s.stats = reinterpret_cast<Stats*>(s.grid + (size_t)ndim * (2 * K + 1));
+    s.hist = reinterpret_cast<double*>(s.stats + 32);
+    s.wf = s.hist + (size_t)nw * K * 32;
+    s.bins = reinterpret_cast<uint32_t*>(s.wf + nw * 32);
+    return s;
+}
+
+// ------------------------------------------------------------------ VEGAS sample (+ fused integrand)
+__global__ void __launch_bounds__(256) vegas_sample_kernel(const __grid_constant__ Dens dens,
+                                                           const __grid_constant__ SampleArgs a) {
+    extern __shared__ double smem_raw[];
+    const int ndim = a.ndim, K = a.K;
+    const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const SmemLayout s = carve(smem_raw, ndim, K, nw);
+    const bool fused = dens.kind != HEPMC_NONE;
+
+    for (int i = threadIdx.x; i < ndim * (2 * K + 1); i += blockDim.x) s.grid[i] = a.grid[i];
+    if (fused)
+        for (int i = threadIdx.x; i < nw * K * 32; i += blockDim.x) s.hist[i] = 0.0;
+    __syncthreads();
+
+    double* hist_w = s.hist + (size_t)warp * K * 32;
+    double* wf_w = s.wf + warp * 32;
+    uint32_t* bins_w = s.bins + warp * 32 * kBinWords;
+
+    const PhiloxKey key = philox_expand(a.seed);
+    const bool replay = a.u_replay != nullptr;
+    const int64_t chunk0 = (int64_t)blockIdx.x * a.chunk;
+    const int ppt = (int)(a.chunk / blockDim.x);
+    const int ncalls = (ndim + 1) >> 1;
+    const int stride = 2 * K + 1;
+    ShiftedAcc acc;
+    acc.init();
+
+    for (int it = 0; it < ppt; ++it) {
+        const int64_t li = chunk0 + (int64_t)it * blockDim.x + threadIdx.x;
+        const bool valid = li < a.n;
+        double wf = 0.0;
+        uint32_t packed[kBinWords - 1];
+#pragma unroll
+        for (int q = 0; q < kBinWords - 1; ++q) packed[q] = 0u;
+        if (valid) {
+            const uint64_t g = (uint64_t)(a.first_index + li);
+            PdfAcc pa;
+            pa.init();
+            double w = 1.0;
+            for (int call = 0; call < ncalls; ++call) {
+                U4 r{0u, 0u, 0u, 0u};
+                if (!replay) r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)call, a.stream_id, key);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int d = 2 * call + h;
+                    if (d < ndim) {
+                        uint32_t bin;
+                        double frac;
+                        if (replay) {
+                            bin = (uint32_t)a.idx_replay[(int64_t)d * a.n + li];
+                            frac = a.u_replay[(int64_t)d * a.n + li];
+                        } else {
+                            bin_frac(h ? r.z : r.x, h ? r.w : r.y, (uint32_t)K, bin, frac);
+                        }
+                        const double* gd = s.grid + d * stride;
+                        const double sz = gd[K + 1 + bin];
+                        const double x = gd[bin] + sz * frac;  // stratified_volume.py:119-121
+                        w *= sz;                               // vegas.py:69-70
+                        if (fused) pdf_acc_dim(dens, pa, d, x);
+#pragma unroll
+                        for (int q = 0; q < kBinWords - 1; ++q)
+                            if (q == (d >> 2)) packed[q] |= bin << (8 * (d & 3));
+                        if (a.x_out) a.x_out[(int64_t)d * a.n + li] = x;
+                        if (a.idx_out) a.idx_out[(int64_t)d * a.n + li] = (int64_t)bin;
+                    }
+                }
+            }
+            w *= a.kpow;  // vegas.py:72 (partition_count evaluated in floating point, App. B1)
+            if (a.w_out) a.w_out[li] = w;
+            if (fused) {
+                const double f = pdf_acc_finish(dens, pa);
+                wf = f * w;  // vegas.py:104
+                acc.add(wf);
+                if (a.f_out) a.f_out[li] = f;
+            }
+        }
+        if (fused) {
+            wf_w[lane] = wf;
+#pragma unroll
+            for (int q = 0; q < kBinWords - 1; ++q)
+                if (q * 4 < ndim) bins_w[lane * kBinWords + q] = packed[q];
+            __syncwarp();
+            warp_hist_update(hist_w, wf_w, bins_w, ndim, lane);
+            __syncwarp();
+        }
+    }
+    if (!fused) return;
+    __syncthreads();
+    block_hist_flush(s.hist, ndim, K, nw, a.hist_partials + (size_t)blockIdx.x * ndim * K);
+    // per-thread -> warp -> block (fixed order)
+    Stats st = warp_merge(acc.stats());
+    if (lane == 0) s.stats[warp] = st;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Stats r{0.0, 0.0, 0.0};
+        for (int w = 0; w < nw; ++w) r = merge(r, s.stats[w]);
+        double* o = a.stats_partials + (size_t)blockIdx.x * 3;
+        o[0] = r.n; o[1] = r.mean; o[2] = r.m2;
+    }
+}
+
+// ------------------------------------------------------------------ two-kernel path: accumulate
+__global__ void __launch_bounds__(256) vegas_accumulate_kernel(const __grid_constant__ SampleArgs a) {
+    extern __shared__ double smem_raw[];
+    const int ndim = a.ndim, K = a.K;
+    const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const SmemLayout s = carve(smem_raw, 0, K, nw);  // no grid needed
+    for (int i = threadIdx.x; i < nw * K * 32; i += blockDim.x) s.hist[i] = 0.0;
+    __syncthreads();
+    double* hist_w = s.hist + (size_t)warp * K * 32;
+    double* wf_w = s.wf + warp * 32;
+    uint32_t* bins_w = s.bins + warp * 32 * kBinWords;
+    const int64_t chunk0 = (int64_t)blockIdx.x * a.chunk;
+    const int ppt = (int)(a.chunk / blockDim.x);
+    ShiftedAcc acc;
+    acc.init();
+    for (int it = 0; it < ppt; ++it) {
+        const int64_t li = chunk0 + (int64_t)it * blockDim.x + threadIdx.x;
+        const bool valid = li < a.n;
+        double wf = 0.0;
+        for (int q = 0; q * 4 < ndim; ++q) {
+            uint32_t word = 0u;
+            if (valid)
+                for (int b = 0; b < 4 && q * 4 + b < ndim; ++b)
+                    word |= ((uint32_t)a.idx_in[(int64_t)(q * 4 + b) * a.n + li] & 0xffu) << (8 * b);
+            bins_w[lane * kBinWords + q] = word;
+        }
+        if (valid) {
+            wf = a.f_in[li] * a.w_in[li];
+            acc.add(wf);
+        }
+        wf_w[lane] = wf;
+        __syncwarp();
+        warp_hist_update(hist_w, wf_w, bins_w, ndim, lane);
+        __syncwarp();
+    }
+    __syncthreads();
+    block_hist_flush(s.hist, ndim, K, nw, a.hist_partials + (size_t)blockIdx.x * ndim * K);
+    Stats st = warp_merge(acc.stats());
+    if (lane == 0) s.stats[warp] = st;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Stats r{0.0, 0.0, 0.0};
+        for (int w = 0; w < nw; ++w) r = merge(r, s.stats[w]);
+        double* o = a.stats_partials + (size_t)blockIdx.x * 3;
+        o[0] = r.n; o[1] = r.mean; o[2] = r.m2;
+    }
+}
+
+// ------------------------------------------------------------------ plain MC
+__global__ void __launch_bounds__(256) plain_sample_kernel(const __grid_constant__ Dens dens,
+                                                           const __grid_constant__ SampleArgs a) {
+    __shared__ Stats s_stats[8];
+    const int ndim = a.ndim;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool fused = dens.kind != HEPMC_NONE;
+    const PhiloxKey key = philox_expand(a.seed);
+    const bool replay = a.u_replay != nullptr;
+    const int64_t chunk0 = (int64_t)blockIdx.x * a.chunk;
+    const int ppt = (int)(a.chunk / blockDim.x);
+    const int ncalls = (ndim + 1) >> 1;
+    ShiftedAcc acc;
+    acc.init();
+    for (int it = 0; it < ppt; ++it) {
+        const int64_t li = chunk0 + (int64_t)it * blockDim.x + threadIdx.x;
+        if (li >= a.n) break;
+        const uint64_t g = (uint64_t)(a.first_index + li);
+        PdfAcc pa;
+        pa.init();
+        for (int call = 0; call < ncalls; ++call) {
+            U4 r{0u, 0u, 0u, 0u};
+            if (!replay) r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)call, a.stream_id, key);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int d = 2 * call + h;
+                if (d < ndim) {
+                    const double x = replay ? a.u_replay[li * ndim + d] : u52(h ? r.z : r.x, h ? r.w : r.y);
+                    if (fused) pdf_acc_dim(dens, pa, d, x);
+                    if (a.x_out) a.x_out[li * ndim + d] = x;  // (N, ndim) row-major, integration.py:45
+                }
+            }
+        }
+        if (fused) {
+            const double f = pdf_acc_finish(dens, pa);
+            acc.add(f);
+            if (a.f_out) a.f_out[li] = f;
+        }
+    }
+    if (!fused) return;
+    Stats st = warp_merge(acc.stats());
+    if (lane == 0) s_stats[warp] = st;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Stats r{0.0, 0.0, 0.0};
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = merge(r, s_stats[w]);
+        double* o = a.stats_partials + (size_t)blockIdx.x * 3;
+        o[0] = r.n; o[1] = r.mean; o[2] = r.m2;
+    }
+}
+
+// values (optionally / weights) -> chunk partials; importance.py:47-50
+__global__ void __launch_bounds__(256) stats_partials_kernel(const double* __restrict__ values,
+                                                             const double* __restrict__ weights, double wscalar,
+                                                             int64_t n, int64_t chunk, double* __restrict__ partials) {
+    __shared__ Stats s_stats[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t chunk0 = (int64_t)blockIdx.x * chunk;
+    const int ppt = (int)(chunk / blockDim.x);
+    ShiftedAcc acc;
+    acc.init();
+    for (int it = 0; it < ppt; ++it) {
+        const int64_t li = chunk0 + (int64_t)it * blockDim.x + threadIdx.x;
+        if (li >= n) break;
+        double v = values[li];
+        if (weights) v = v / weights[li];
+        else if (wscalar != 1.0) v = v / wscalar;
+        acc.add(v);
+    }
+    Stats st = warp_merge(acc.stats());
+    if (lane == 0) s_stats[warp] = st;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Stats r{0.0, 0.0, 0.0};
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = merge(r, s_stats[w]);
+        double* o = partials + (size_t)blockIdx.x * 3;
+        o[0] = r.n; o[1] = r.mean; o[2] = r.m2;
+    }
+}
+
+// ------------------------------------------------------------------ ordered reductions
+constexpr int kMaxOut = 64;
+struct RowRanges {
+    int64_t begin[kMaxOut + 1];
+    int n_out;
+};
+
+// one warp per output slot: lane l merges a contiguous sub-range in row order, then the
+// 32 lane results are merged in lane order.  The tree depends on the range only.
+__global__ void __launch_bounds__(32) reduce_stats_kernel(const double* __restrict__ rows,
+                                                          const __grid_constant__ RowRanges rr,
+                                                          double* __restrict__ out) {
+    const int s = blockIdx.x, lane = threadIdx.x;
+    const int64_t b = rr.begin[s], e = rr.begin[s + 1];
+    const int64_t len = e - b;
+    const int64_t per = (len + 31) / 32;
+    int64_t r0 = b + lane * per, r1 = r0 + per;
+    if (r0 > e) r0 = e;
+    if (r1 > e) r1 = e;
+    Stats acc{0.0, 0.0, 0.0};
+    for (int64_t r = r0; r < r1; ++r) {
+        Stats t{rows[r * 3], rows[r * 3 + 1], rows[r * 3 + 2]};
+        acc = merge(acc, t);
+    }
+    Stats total{0.0, 0.0, 0.0};
+    for (int l = 0; l < 32; ++l) {
+        Stats t;
+        t.n = __shfl_sync(0xffffffffu, acc.n, l);
+        t.mean = __shfl_sync(0xffffffffu, acc.mean, l);
+        t.m2 = __shfl_sync(0xffffffffu, acc.m2, l);
+        total = merge(total, t);
+    }
+    if (lane == 0) {
+        out[s * 3] = total.n;
+        out[s * 3 + 1] = total.mean;
+        out[s * 3 + 2] = total.m2;
+    }
+}
+
+// out[s][col] = sum over rows of slot s, in row order; 4 interleaved sub-sums per column
+// (fixed: row index mod 4) combined as ((s0+s1)+(s2+s3)) to shorten the dependent chain.
+__global__ void __launch_bounds__(128) reduce_hist_kernel(const double* __restrict__ rows,
+                                                          const __grid_constant__ RowRanges rr, int ncols,
+                                                          double* __restrict__ out) {
+    const int s = blockIdx.y;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncols) return;
+    const int64_t b = rr.begin[s], e = rr.begin[s + 1];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int64_t r = b;
+    for (; r + 3 < e; r += 4) {
+        s0 += rows[r * ncols + col];
+        s1 += rows[(r + 1) * ncols + col];
+        s2 += rows[(r + 2) * ncols + col];
+        s3 += rows[(r + 3) * ncols + col];
+    }
+    if (r < e) s0 += rows[r * ncols + col];
+    if (r + 1 < e) s1 += rows[(r + 1) * ncols + col];
+    if (r + 2 < e) s2 += rows[(r + 2) * ncols + col];
+    out[(size_t)s * ncols + col] = (s0 + s1) + (s2 + s3);
+}
+
+// ------------------------------------------------------------------ grid adaptation (one CTA)
+__global__ void __launch_bounds__(256) vegas_update_kernel(const double* __restrict__ slot_stats,
+                                                           const double* __restrict__ slot_hist, int n_slots,
+                                                           double* __restrict__ grid, int ndim, int K, double c,
+                                                           int j, double* __restrict__ est_var) {
+    extern __shared__ double sm[];
+    double* s_new = sm;  // ndim*K new sizes
+    __shared__ double s_est, s_n;
+    if (threadIdx.x == 0) {
+        Stats t{0.0, 0.0, 0.0};
+        for (int s = 0; s < n_slots; ++s) {
+            Stats u{slot_stats[s * 3], slot_stats[s * 3 + 1], slot_stats[s * 3 + 2]};
+            t = merge(t, u);
+        }
+        s_est = t.mean;               // est_j = mean(weighted)           vegas.py:110
+        s_n = t.n;
+        est_var[2 * j] = t.mean;
+        est_var[2 * j + 1] = t.m2 / t.n / t.n;  // var_j = var0(weighted)/N   vegas.py:111
+    }
+    __syncthreads();
+    const double est = s_est, n = s_n;
+    const int stride = 2 * K + 1;
+    const double inertia = (double)j;
+    for (int q = threadIdx.x; q < ndim * K; q += blockDim.x) {
+        const int d = q / K, k = q % K;
+        double h = 0.0;
+        for (int s = 0; s < n_slots; ++s) h += slot_hist[(size_t)s * ndim * K + q];
+        const double estimate = h / n;                       // vegas.py:108-109
+        const double size = grid[d * stride + K + 1 + k];
+        const double old_v = est / size;                     // vegas.py:113
+        const double new_v = (double)K * estimate;
+        // damped_update, helper.py:71-72
+        const double inv = new_v * c / (inertia + 1.0 + c) + old_v * (inertia + 1.0) / (inertia + 1.0 + c);
+        s_new[q] = 1.0 / inv;                                // vegas.py:115
+    }
+    __syncthreads();
+    if (threadIdx.x < ndim) {
+        const int d = threadIdx.x;
+        double tot = 0.0;
+        for (int k = 0; k < K; ++k) tot += s_new[d * K + k];
+        double* gd = grid + d * stride;
+        double cum = 0.0;
+        gd[0] = 0.0;                                         // App. B2: bounds[d][0] = 0
+        for (int k = 0; k < K; ++k) {
+            const double sz = s_new[d * K + k] / tot;        // vegas.py:117
+            gd[K + 1 + k] = sz;
+            cum += sz;                                       // np.cumsum, stratified_volume.py:167
+            gd[k + 1] = cum;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ GridVolumes.pdf
+__global__ void __launch_bounds__(256) grid_pdf_kernel(const double* __restrict__ grid, int ndim, int K, double kpow,
+                                                       const double* __restrict__ xs, int64_t n,
+                                                       double* __restrict__ out) {
+    extern __shared__ double s_grid[];
+    const int stride = 2 * K + 1;
+    for (int i = threadIdx.x; i < ndim * stride; i += blockDim.x) s_grid[i] = grid[i];
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        bool inside = true;
+        double vol = 1.0;
+        for (int d = 0; d < ndim; ++d) {
+            const double x = xs[i * ndim + d];
+            inside = inside && (0.0 < x) && (x < 1.0);
+            const double* b = s_grid + d * stride;
+            // np.argmax(x < bounds) - 1 (stratified_volume.py:80-81); all-False -> -1 -> last bin
+            int idx = -1;
+            for (int k = 0; k <= K; ++k)
+                if (x < b[k]) { idx = k - 1; break; }
+            if (idx < 0) idx = K - 1;
+            vol *= b[K + 1 + idx];
+        }
+        out[i] = inside ? 1.0 / kpow / vol : 0.0;  // pdf_indices :67-72 with default counts
+    }
+}
+
+static int fill_ranges(RowRanges& rr, const int64_t* row_begin_host, int n_out, const char* who) {
+    HEPMC_REQUIRE(row_begin_host != nullptr && n_out >= 1 && n_out <= kMaxOut, HEPMC_E_ARG,
+                  "%s: n_out=%d outside [1,%d] or NULL ranges", who, n_out, kMaxOut);
+    rr.n_out = n_out;
+    for (int i = 0; i <= n_out; ++i) rr.begin[i] = row_begin_host[i];
+    for (int i = 0; i < n_out; ++i)
+        HEPMC_REQUIRE(rr.begin[i] <= rr.begin[i + 1], HEPMC_E_ARG, "%s: row ranges must be non-decreasing", who);
+    return 0;
+}
+
+static int pick_threads(int ndim, int K, size_t& smem) {
+    int dev = 0, maxs = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&maxs, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    for (int t = 256; t >= 64; t >>= 1) {
+        smem = vegas_smem_bytes(ndim, K, t);
+        if ((int64_t)smem <= (int64_t)maxs) return t;
+    }
+    return 0;
+}
+
+static int check_sample_common(const char* who, int ndim, int K, int64_t n, int64_t first_index, int64_t chunk) {
+    HEPMC_REQUIRE(ndim >= 1 && ndim <= HEPMC_MAX_DIM, HEPMC_E_UNSUPPORTED, "%s: ndim %d outside [1,%d]", who, ndim,
+                  HEPMC_MAX_DIM);
+    HEPMC_REQUIRE(K >= 1 && K <= HEPMC_MAX_DIVISIONS, HEPMC_E_UNSUPPORTED, "%s: divisions %d outside [1,%d]", who, K,
+                  HEPMC_MAX_DIVISIONS);
+    HEPMC_REQUIRE(n >= 0 && first_index >= 0, HEPMC_E_ARG, "%s: negative n/first_index", who);
+    HEPMC_REQUIRE(chunk >= 256 && chunk % 256 == 0, HEPMC_E_ARG, "%s: chunk must be a positive multiple of 256", who);
+    HEPMC_REQUIRE(first_index % chunk == 0, HEPMC_E_ARG, "%s: first_index must be a multiple of chunk", who);
+    return 0;
+}
+
+}  // namespace hepmc
+
+using namespace hepmc;
+
+extern "C" {
+
+int64_t hepmc_default_chunk(int64_t n_total) {
+    // a function of the iteration's TOTAL point count only (never of the GPU count)
+    if (n_total >= ((int64_t)1 << 26)) return 32768;
+    if (n_total >= ((int64_t)1 << 21)) return 8192;
+    return 2048;
+}
+
+int hepmc_plain_mc_sample(const hepmc_density_t* dens, int64_t n, int64_t first_index, int64_t chunk,
+                          uint64_t seed, uint32_t stream_id, const double* u_replay_dev,
+                          double* data_dev, double* f_dev, double* partials_dev, void* stream) {
+    HEPMC_REQUIRE(dens != nullptr, HEPMC_E_ARG, "hepmc_plain_mc_sample: dens is NULL");
+    int e = check_sample_common("hepmc_plain_mc_sample", dens->ndim, 1, n, first_index, chunk);
+    if (e) return e;
+    HEPMC_REQUIRE(dens->kind >= HEPMC_CAMEL && dens->kind <= HEPMC_NONE, HEPMC_E_ARG, "bad density kind %d", dens->kind);
+    HEPMC_REQUIRE(dens->kind == HEPMC_NONE || partials_dev, HEPMC_E_ARG, "hepmc_plain_mc_sample: partials_dev is NULL");
+    HEPMC_REQUIRE(dens->kind != HEPMC_NONE || data_dev, HEPMC_E_ARG, "hepmc_plain_mc_sample: nothing to do");
+    if (n == 0) return 0;
+    SampleArgs a{};
+    a.ndim = dens->ndim; a.K = 1; a.n = n; a.first_index = first_index; a.chunk = chunk;
+    a.seed = seed; a.stream_id = stream_id; a.u_replay = u_replay_dev;
+    a.x_out = data_dev; a.f_out = f_dev; a.stats_partials = partials_dev;
+    const int64_t blocks = (n + chunk - 1) / chunk;
+    plain_sample_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(*dens, a);
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+int hepmc_stats_partials(const double* values_dev, const double* weights_dev, double weight_scalar,
+                         int64_t n, int64_t chunk, double* partials_dev, void* stream) {
+    HEPMC_REQUIRE(values_dev && partials_dev && n >= 0, HEPMC_E_ARG, "hepmc_stats_partials: bad arguments");
+    HEPMC_REQUIRE(chunk >= 256 && chunk % 256 == 0, HEPMC_E_ARG, "hepmc_stats_partials: bad chunk");
+    if (n == 0) return 0;
+    const int64_t blocks = (n + chunk - 1) / chunk;
+    stats_partials_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(values_dev, weights_dev, weight_scalar, n,
+                                                                           chunk, partials_dev);
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+int hepmc_reduce_stats(const double* rows_dev, const int64_t* row_begin_host, int n_out,
+                       double* out_dev, void* stream) {
+    RowRanges rr;
+    int e = fill_ranges(rr, row_begin_host, n_out, "hepmc_reduce_stats");
+    if (e) return e;
+    HEPMC_REQUIRE(rows_dev && out_dev, HEPMC_E_ARG, "hepmc_reduce_stats: NULL buffer");
+    reduce_stats_kernel<<<n_out, 32, 0, as_stream(stream)>>>(rows_dev, rr, out_dev);
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+int hepmc_reduce_hist(const double* rows_dev, const int64_t* row_begin_host, int n_out, int ncols,
+                      double* out_dev, void* stream) {
+    RowRanges rr;
+    int e = fill_ranges(rr, row_begin_host, n_out, "hepmc_reduce_hist");
+    if (e) return e;
+    HEPMC_REQUIRE(rows_dev && out_dev && ncols >= 1, HEPMC_E_ARG, "hepmc_reduce_hist: bad arguments");
+    dim3 grid((ncols + 127) / 128, n_out);
+    reduce_hist_kernel<<<grid, 128, 0, as_stream(stream)>>>(rows_dev, rr, ncols, out_dev);
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+int hepmc_vegas_sample(const hepmc_density_t* dens, const double* grid_dev, int ndim, int divisions,
+                       int64_t n, int64_t first_index, int64_t chunk, uint64_t seed, uint32_t stream_id,
+                       const int64_t* idx_replay_dev, const double* u_replay_dev,
+                       double* x_dev, double* f_dev, double* w_dev, int64_t* idx_dev,
+                       double* stats_partials_dev, double* hist_partials_dev, void* stream) {
+    HEPMC_REQUIRE(dens != nullptr && grid_dev != nullptr, HEPMC_E_ARG, "hepmc_vegas_sample: NULL dens/grid");
+    int e = check_sample_common("hepmc_vegas_sample", ndim, divisions, n, first_index, chunk);
+    if (e) return e;
+    HEPMC_REQUIRE(dens->kind >= HEPMC_CAMEL && dens->kind <= HEPMC_NONE, HEPMC_E_ARG, "bad density kind %d", dens->kind);
+    HEPMC_REQUIRE(dens->kind == HEPMC_NONE || dens->ndim == ndim, HEPMC_E_ARG,
+                  "hepmc_vegas_sample: density ndim %d != grid ndim %d", dens->ndim, ndim);
+    HEPMC_REQUIRE((idx_replay_dev == nullptr) == (u_replay_dev == nullptr), HEPMC_E_ARG,
+                  "hepmc_vegas_sample: replay needs both idx and u tapes");
+    const bool fused = dens->kind != HEPMC_NONE;
+    HEPMC_REQUIRE(!fused || (stats_partials_dev && hist_partials_dev), HEPMC_E_ARG,
+                  "hepmc_vegas_sample: partial buffers are NULL");
+    HEPMC_REQUIRE(fused || (x_dev && w_dev && idx_dev), HEPMC_E_ARG,
+                  "hepmc_vegas_sample: two-kernel path needs x, w and idx outputs");
+    if (n == 0) return 0;
+    size_t smem = 0;
+    const int threads = pick_threads(ndim, divisions, smem);
+    HEPMC_REQUIRE(threads > 0, HEPMC_E_UNSUPPORTED, "hepmc_vegas_sample: grid %d x %d does not fit shared memory", ndim,
+                  divisions);
+    HEPMC_REQUIRE(chunk % threads == 0, HEPMC_E_ARG, "chunk not a multiple of the block size");
+    HEPMC_CUDA(cudaFuncSetAttribute(vegas_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SampleArgs a{};
+    a.grid = grid_dev; a.ndim = ndim; a.K = divisions; a.n = n; a.first_index = first_index; a.chunk = chunk;
+    a.seed = seed; a.stream_id = stream_id; a.idx_replay = idx_replay_dev; a.u_replay = u_replay_dev;
+    a.x_out = x_dev; a.f_out = f_dev; a.w_out = w_dev; a.idx_out = idx_dev;
+    a.stats_partials = stats_partials_dev; a.hist_partials = hist_partials_dev;
+    a.kpow = pow((double)divisions, (double)ndim);
+    const int64_t blocks = (n + chunk - 1) / chunk;
+    vegas_sample_kernel<<<(unsigned)blocks, threads, smem, as_stream(stream)>>>(*dens, a);
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+int hepmc_vegas_accumulate(const double* f_dev, const double* w_dev, const int64_t* idx_dev,
+                           int ndim, int divisions, int64_t n, int64_t chunk,
+                           double* stats_partials_dev, double* hist_partials_dev, void* stream) {
+    int e = check_sample_common("hepmc_vegas_accumulate", ndim, divisions, n, 0, chunk);
+    if (e) return e;
+    HEPMC_REQUIRE(f_dev && w_dev && idx_dev && stats_partials_dev && hist_partials_dev, HEPMC_E_ARG,
+                  "hepmc_vegas_accumulate: NULL buffer");
+    if (n == 0) return 0;
+    size_t smem = 0;
+    const int threads = pick_threads(ndim, divisions, smem);
+    HEPMC_REQUIRE(threads > 0, HEPMC_E_UNSUPPORTED, "hepmc_vegas_accumulate: %d divisions do not fit shared memory",
+                  divisions);
+    smem = vegas_smem_bytes(0, divisions, threads);
+    HEPMC_CUDA(cudaFuncSetAttribute(vegas_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SampleArgs a{};
+    a.ndim = ndim; a.K = divisions; a.n = n; a.chunk = chunk;
+    a.f_in = f_dev; a.w_in = w_dev; a.idx_in = idx_dev;
+    a.stats_partials = stats_partials_dev; a.hist_partials = hist_partials_dev;
+    const int64_t blocks = (n + chunk - 1) / chunk;
+    vegas_accumulate_kernel<<<(unsigned)blocks, threads, smem, as_stream(stream)>>>(a);
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+int hepmc_vegas_update_grid(const double* slot_stats_dev, const double* slot_hist_dev, int n_slots,
+                            double* grid_dev, int ndim, int divisions, double c, int j,
+                            double* est_var_dev, void* stream) {
+    HEPMC_REQUIRE(slot_stats_dev && slot_hist_dev && grid_dev && est_var_dev, HEPMC_E_ARG,
+                  "hepmc_vegas_update_grid: NULL buffer");
+    HEPMC_REQUIRE(n_slots >= 1 && ndim >= 1 && ndim <= HEPMC_MAX_DIM && divisions >= 1 && j >= 0, HEPMC_E_ARG,
+                  "hepmc_vegas_update_grid: bad sizes");
+    const size_t smem = (size_t)ndim * divisions * 8;
+    HEPMC_CUDA(cudaFuncSetAttribute(vegas_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vegas_update_kernel<<<1, 256, smem, as_stream(stream)>>>(slot_stats_dev, slot_hist_dev, n_slots, grid_dev, ndim,
+                                                             divisions, c, j, est_var_dev);
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+static void slot_ranges(int64_t n_chunks, int64_t* begin /* HEPMC_N_SLOTS+1 */) {
+    for (int s = 0; s <= HEPMC_N_SLOTS; ++s) begin[s] = (n_chunks * s) / HEPMC_N_SLOTS;
+}
+
+int64_t hepmc_vegas_workspace_bytes(int ndim, int divisions, int64_t n) {
+    const int64_t chunk = hepmc_default_chunk(n);
+    const int64_t nc = (n + chunk - 1) / chunk;
+    const int64_t cols = (int64_t)ndim * divisions;
+    return 8 * (nc * 3 + nc * cols + HEPMC_N_SLOTS * 3 + HEPMC_N_SLOTS * cols) + 256;
+}
+
+int hepmc_vegas_integrate(const hepmc_density_t* dens, double* grid_dev, int ndim, int divisions,
+                          int64_t n, int iterations, double c, uint64_t seed, uint32_t stream_id0,
+                          double* est_var_dev, void* workspace_dev, int64_t workspace_bytes,
+                          void* stream) {
+    HEPMC_REQUIRE(dens && grid_dev && est_var_dev && workspace_dev, HEPMC_E_ARG, "hepmc_vegas_integrate: NULL buffer");
+    HEPMC_REQUIRE(dens->kind != HEPMC_NONE, HEPMC_E_ARG, "hepmc_vegas_integrate needs a built-in integrand");
+    HEPMC_REQUIRE(n > 0 && iterations >= 1, HEPMC_E_ARG, "hepmc_vegas_integrate: n and iterations must be positive");
+    HEPMC_REQUIRE(workspace_bytes >= hepmc_vegas_workspace_bytes(ndim, divisions, n), HEPMC_E_ARG,
+                  "hepmc_vegas_integrate: workspace too small");
+    const int64_t chunk = hepmc_default_chunk(n);
+    const int64_t nc = (n + chunk - 1) / chunk;
+    const int64_t cols = (int64_t)ndim * divisions;
+    double* ws = reinterpret_cast<double*>(workspace_dev);
+    double* stats_p = ws;
+    double* hist_p = stats_p + nc * 3;
+    double* slot_stats = hist_p + nc * cols;
+    double* slot_hist = slot_stats + HEPMC_N_SLOTS * 3;
+    int64_t begin[HEPMC_N_SLOTS + 1];
+    slot_ranges(nc, begin);
+    for (int j = 0; j < iterations; ++j) {
+        int e = hepmc_vegas_sample(dens, grid_dev, ndim, divisions, n, 0, chunk, seed, stream_id0 + (uint32_t)j,
+                                   nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats_p, hist_p, stream);
+        if (e) return e;
+        e = hepmc_reduce_stats(stats_p, begin, HEPMC_N_SLOTS, slot_stats, stream);
+        if (e) return e;
+        e = hepmc_reduce_hist(hist_p, begin, HEPMC_N_SLOTS, (int)cols, slot_hist, stream);
+        if (e) return e;
+        e = hepmc_vegas_update_grid(slot_stats, slot_hist, HEPMC_N_SLOTS, grid_dev, ndim, divisions, c, j,
+                                    est_var_dev, stream);
+        if (e) return e;
+    }
+    return 0;
+}
+
+int hepmc_grid_pdf(const double* grid_dev, int ndim, int divisions, const double* xs_dev,
+                   int64_t n, double* out_dev, void* stream) {
+    HEPMC_REQUIRE(grid_dev && ndim >= 1 && ndim <= HEPMC_MAX_DIM && divisions >= 1 && n >= 0, HEPMC_E_ARG,
+                  "hepmc_grid_pdf: bad arguments");
+    if (n == 0) return 0;
+    HEPMC_REQUIRE(xs_dev && out_dev, HEPMC_E_ARG, "hepmc_grid_pdf: NULL buffer");
+    const size_t smem = (size_t)ndim * (2 * divisions + 1) * 8;
+    HEPMC_CUDA(cudaFuncSetAttribute(grid_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    grid_pdf_kernel<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(grid_dev, ndim, divisions,
+                                                                         pow((double)divisions, (double)ndim), xs_dev, n,
+                                                                         out_dev);
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+"""Hamiltonian Monte Carlo (mirror of hepmc/hamiltonian/hmc.py:23-109).
+
+`HamiltonianUpdate(target_density, p_dist, steps, step_size)`: per transition draw
+p ~ p_dist, leapfrog, accept with  pdf(q') N(p') / (pdf(q) N(p))  (NaN -> reject).
+Device kernel requirements: `target_density` built-in (its pdf drives the Metropolis
+test in float64), `p_dist` = densities.Gaussian with diagonal covariance and zero mean,
+gradient = the target's own `pot_gradient` or an ELM surrogate attached with
+`surrogate.attach_surrogate_gradient` / by assigning a `SurrogateGradient` to
+`target_density.pot_gradient` (the wiring of interfaces/mc3_hmc_el.py:32-35).
+"""
+import numpy as np
+
+from ..core.markov.metropolis import MetropolisUpdate
+from ..core.markov import ensemble
+from ..core.density import BuiltinDensity
+from ..core.densities import Gaussian
+from .simulation import HamiltonLeapfrog
+from .. import _lib
+
+
+class HamiltonianUpdate(MetropolisUpdate):
+
+    def __init__(self, target_density, p_dist, steps, step_size, simulate=None,
+                 sim_class=HamiltonLeapfrog, is_adaptive=False, precision="f64"):
+        """:param precision: arithmetic of a SURROGATE gradient: "f64" (parity), "f32"
+        (SIMT single precision) or "tc" (tcgen05 tensor cores).  The exact gradient and
+        the Metropolis test are always float64."""
+        super().__init__(target_density.ndim, target_density.pdf, is_adaptive)
+        self.p_dist = p_dist
+        self.target_density = target_density
+        self.precision = precision
+        if simulate is None:
+            self.simulate = sim_class(target_density.pot_gradient, p_dist.pot_gradient, step_size, steps)
+        else:
+            self.simulate = simulate
+
+    def proposal_pdf(self, state, candidate):
+        pass
+
+    @property
+    def step_size(self):
+        return self.simulate.step_size
+
+    @step_size.setter
+    def step_size(self, step_size):
+        self.simulate.step_size = step_size
+
+    @property
+    def steps(self):
+        return self.simulate.steps
+
+    @steps.setter
+    def steps(self, steps):
+        self.simulate.steps = steps
+
+    def _run_ensemble(self, x0, sample_size, thin, store_chain, first_chain, replay):
+        from ..surrogate.extreme_learning import SurrogateGradient
+        tgt = self.target_density
+        if not isinstance(tgt, BuiltinDensity) or "pdf" in vars(tgt):
+            raise TypeError("HamiltonianUpdate on the device needs a built-in target density; "
+                            "there is no CPU fallback.")
+        if not isinstance(self.p_dist, Gaussian):
+            raise TypeError("the momentum distribution must be densities.Gaussian")
+        if np.any(self.p_dist.mean != 0):
+            raise TypeError("the momentum distribution must have zero mean")
+        mass = self.p_dist._diag()
+        grad = vars(tgt).get("pot_gradient", None)
+        grad = getattr(grad, "fn", grad)            # unwrap util.count_calls
+        elm_blk, keep = None, None
+        if grad is not None:
+            if not isinstance(grad, SurrogateGradient):
+                raise TypeError("a replaced pot_gradient must be a surrogate.SurrogateGradient "
+                                "(ELM surrogate); arbitrary Python gradients cannot run in the kernel")
+            elm_blk, keep = grad.block()
+        prec = {"f64": 0, "f32": 1, "tc": 2}[self.precision]
+        if elm_blk is None:
+            prec = 0
+        out = ensemble.run_hmc(tgt._block(), elm_blk, prec, x0, mass, self.step_size, self.steps,
+                               sample_size, thin, store_chain, first_chain, None, replay)
+        del keep
+        return out
+
+    def sample(self, sample_size, initial, out_mask=None, log_every=5000, **kwargs):
+        sample = super().sample(sample_size, initial, out_mask, log_every, **kwargs)
+        sample.target = self.target_density
+        return sample

@@ -1,0 +1,74 @@
+"""One process per GPU: partition of the work and the (tiny) exchange step.
+
+Points / chains are identified by GLOBAL indices (Philox counters), so sharding is a
+choice of index ranges.  Reductions use a FIXED set of N_SLOTS = 8 slots over the chunk
+range of a call; each rank owns whole slots, slot partials are all-gathered (a few KB
+over NVLink via NCCL; gloo in the CPU tests) and merged in slot order on every rank.
+The reduction tree is therefore a function of the problem only and results are
+bit-identical at 1, 2, 4 or 8 GPUs.
+"""
+import torch
+import torch.distributed as dist
+
+from ._lib import N_SLOTS
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def slot_span(rank=None, world_size=None):
+    """Slots [s0, s1) owned by this rank."""
+    if rank is None:
+        rank, world_size = world()
+    if N_SLOTS % world_size:
+        raise RuntimeError("world size %d must divide the %d reduction slots" % (world_size, N_SLOTS))
+    per = N_SLOTS // world_size
+    return rank * per, (rank + 1) * per
+
+
+def slot_begins(n_chunks):
+    """Chunk index where each slot starts (N_SLOTS + 1 entries)."""
+    return [(n_chunks * s) // N_SLOTS for s in range(N_SLOTS + 1)]
+
+
+def local_span(n_total, chunk, rank=None, world_size=None):
+    """This rank's part of a call over n_total items cut into chunks of `chunk`:
+    returns (first_index, n_local, local_slot_begins) where local_slot_begins are the
+    chunk offsets (relative to the rank's first chunk) of its slots."""
+    n_chunks = (n_total + chunk - 1) // chunk
+    begins = slot_begins(n_chunks)
+    s0, s1 = slot_span(rank, world_size)
+    c0, c1 = begins[s0], begins[s1]
+    first = c0 * chunk
+    n_local = max(0, min(n_total, c1 * chunk) - first)
+    return first, n_local, [b - c0 for b in begins[s0:s1 + 1]]
+
+
+def item_span(n_total, rank=None, world_size=None):
+    """Contiguous split of n_total independent items (chains, RAMBO points): (first, count)."""
+    if rank is None:
+        rank, world_size = world()
+    first = (n_total * rank) // world_size
+    last = (n_total * (rank + 1)) // world_size
+    return first, last - first
+
+
+def gather_slots(local_rows):
+    """(n_local_slots, P) on every rank -> (N_SLOTS, P), slot order, on every rank."""
+    rank, ws = world()
+    if ws == 1:
+        return local_rows
+    out = torch.empty((N_SLOTS, local_rows.shape[1]), dtype=local_rows.dtype, device=local_rows.device)
+    dist.all_gather_into_tensor(out, local_rows.contiguous())
+    return out
+
+
+def sum_int(value_tensor):
+    """All-reduce (sum) of integer counters; order-independent, hence deterministic."""
+    rank, ws = world()
+    if ws > 1:
+        dist.all_reduce(value_tensor, op=dist.ReduceOp.SUM)
+    return value_tensor

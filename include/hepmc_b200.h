@@ -1,0 +1,246 @@
+/*
+ * hepmc_b200 -- C ABI of the B200-native hot path of hepmc (mathisgerdes/hep-monte-carlo).
+ *
+ * The reference is pure Python/NumPy: it has NO plugin/FFI layer.  The
+ * drop-in boundary is therefore its Python class API (hepmc_b200/ mirrors it) and THIS
+ * header is what that mirror -- or any other host language -- binds.  Each entry point
+ * names the reference function (path relative to /root/reference/src/hepmc/, file:line)
+ * whose NumPy body it replaces.
+ *
+ * Conventions
+ *   - every pointer named *_dev is DEVICE memory owned by the caller (e.g. a torch CUDA
+ *     tensor's data_ptr()); nothing is allocated, retained or freed by the library
+ *     except the explicitly documented workspaces the caller also passes in;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every
+ *     call only ENQUEUES work on it and returns without synchronising, unless stated;
+ *   - all arithmetic is IEEE float64; indices are int64 unless stated;
+ *   - return value: 0 on success, a negative HEPMC_E_* code for argument errors, or a
+ *     positive cudaError_t; hepmc_last_error() returns a thread-local message;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * RNG: Philox4x32-10 (Random123).  key = 64-bit seed; counter = (item index lo, item
+ * index hi, draw-block index inside the item, stream id).  An "item" is a sample point
+ * (integrators, RAMBO) or a chain (samplers) identified by its GLOBAL index, so any
+ * partition of the index range over GPUs reproduces the same draws.
+ */
+#ifndef HEPMC_B200_H
+#define HEPMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HEPMC_B200_ABI_VERSION 1
+#define HEPMC_MAX_DIM 32          /* max dimensionality of a built-in density      */
+#define HEPMC_MAX_DIVISIONS 255   /* max VEGAS bins per axis (bin ids are bytes)    */
+#define HEPMC_N_SLOTS 8           /* fixed reduction slots: GPU-count invariance    */
+
+/* error codes (negative); positive values are cudaError_t */
+#define HEPMC_E_ARG (-1)          /* bad argument (null pointer, size, kind)        */
+#define HEPMC_E_UNSUPPORTED (-2)  /* shape outside what the kernels are built for   */
+#define HEPMC_E_NODEVICE (-3)     /* no CUDA device                                 */
+
+/* built-in analytic densities: core/densities/{camel,banana,gaussian,uniform}.py */
+enum hepmc_density_kind {
+    HEPMC_CAMEL = 0,    /* Camel: two-Gaussian mixture restricted to the open unit cube (camel.py:83-100) */
+    HEPMC_UCAMEL = 1,   /* UnconstrainedCamel (camel.py:9-45)                                           */
+    HEPMC_BANANA = 2,   /* Banana (banana.py:8-51)                                                      */
+    HEPMC_GAUSSIAN = 3, /* Gaussian with diagonal covariance (gaussian.py:8-76)                         */
+    HEPMC_UNIFORM = 4,  /* Uniform on the open box (low, high)^ndim (uniform.py:7-34)                   */
+    HEPMC_NONE = 5      /* no fused integrand: sample/weight only (two-kernel path)                     */
+};
+
+/* Parameter block of a built-in density (host struct, passed by pointer, copied into
+ * kernel parameters).  Filled by the host mirror exactly the way SciPy's
+ * multivariate_normal prepares its constants:
+ *   CAMEL/UCAMEL: a[d]=mu_a, b[d]=mu_b, s0=sqrt(1/cov), s1=n*log(2pi)+n*log(cov), s2=cov
+ *   BANANA:       s0=bananicity b, a[d]=sqrt(1/cov_d) with cov=(100,1,..,1), s1=n*log(2pi)+log(100)
+ *   GAUSSIAN:     a[d]=mean, b[d]=sqrt(1/cov_d), c[d]=1/cov_d, s1=n*log(2pi)+sum(log cov_d)
+ *   UNIFORM:      s0=low, s1=high, s2=volume
+ */
+typedef struct hepmc_density {
+    int32_t kind;
+    int32_t ndim;
+    double a[HEPMC_MAX_DIM];
+    double b[HEPMC_MAX_DIM];
+    double c[HEPMC_MAX_DIM];
+    double s0, s1, s2, s3;
+} hepmc_density_t;
+
+enum hepmc_eval_what {
+    HEPMC_PDF = 0,          /* Density.pdf           density.py:70   -> (N,)      */
+    HEPMC_POT = 1,          /* Density.pot           density.py:48   -> (N,)      */
+    HEPMC_POT_GRADIENT = 2, /* Density.pot_gradient  density.py:55   -> (N,ndim)  */
+    HEPMC_PDF_GRADIENT = 3  /* Density.pdf_gradient  density.py:73   -> (N,ndim)  */
+};
+
+/* ---- library / device ------------------------------------------------------------ */
+int hepmc_abi_version(void);
+const char* hepmc_last_error(void);
+/* out[0]=SM count, out[1]=cc major, out[2]=cc minor, out[3]=max smem/block optin, out[4]=SM clock kHz */
+int hepmc_device_info(int device, int64_t* out5);
+/* FP64 DFMA micro-benchmark used as the FP64-SIMT roofline denominator.  Runs
+ * `iters` dependent-chain rounds of 8 independent DFMAs per thread on a full grid, and
+ * returns the elapsed milliseconds (CUDA events, synchronises) and the flop count. */
+int hepmc_fp64_probe(int64_t iters, double* ms_out, double* flops_out, void* stream);
+
+/* ---- densities: replaces Density.pdf/pot/pot_gradient/pdf_gradient ---------------- */
+/* xs_dev: (n, ndim) row-major.  out_dev: (n,) or (n, ndim).
+ * Replaces camel.py:20-45,87-100; banana.py:13-51; gaussian.py:30-47; uniform.py:15-31;
+ * generic rules density.py:48-68 (pot=-log pdf, NaN->inf; pot_gradient=inf where pdf==0).
+ * BANANA pot follows the reference's sign (returns +log pdf, banana.py:35). */
+int hepmc_density_eval(const hepmc_density_t* dens, int what, const double* xs_dev,
+                       int64_t n, double* out_dev, void* stream);
+
+/* ---- plain Monte Carlo: replaces PlainMC.__call__ integration.py:28-50 ------------ */
+/* Deterministic reduction unit: one CTA processes one CHUNK of consecutive points with a
+ * fixed point->thread mapping and writes one partial row.  The chunk size must be a
+ * function of the call's TOTAL point count only (never of the GPU count); this is the
+ * library's choice.  Always a multiple of 256. */
+int64_t hepmc_default_chunk(int64_t n_total);
+
+/* Points first_index .. first_index+n-1 of the global stream.  Native RNG unless
+ * u_replay_dev (n, ndim) is given (the reference's own np.random.random draws).
+ * Optional outputs data_dev (n, ndim), f_dev (n,).  Per-chunk deterministic partials
+ * (count, mean, M2) are written to partials_dev[(n_chunks) x 3], n_chunks =
+ * ceil(n / chunk); chunk boundaries are relative to first_index, which must be a
+ * multiple of chunk.  dens->kind == HEPMC_NONE: draw data only (two-kernel path). */
+int hepmc_plain_mc_sample(const hepmc_density_t* dens, int64_t n, int64_t first_index, int64_t chunk,
+                          uint64_t seed, uint32_t stream_id, const double* u_replay_dev,
+                          double* data_dev, double* f_dev, double* partials_dev, void* stream);
+
+/* Generic ordered reduction of (count, mean, M2) rows: rows [row_begin[s], row_begin[s+1])
+ * -> out_dev[s*3 .. s*3+2] for s < n_out, merged in row order (Chan et al.).  Used for the
+ * slot partials of every integrator and for the final combine (n_out = 1).
+ * Replaces the np.mean / np.var(ddof=0) pair of integration.py:47-48, importance.py:47-50,
+ * vegas.py:110-111. */
+int hepmc_reduce_stats(const double* rows_dev, const int64_t* row_begin_host, int n_out,
+                       double* out_dev, void* stream);
+
+/* mean/var of values[i] (optionally values[i]/weights[i]) for the two-kernel path:
+ * per-chunk partials like hepmc_plain_mc_sample.  importance.py:47-50. */
+int hepmc_stats_partials(const double* values_dev, const double* weights_dev, double weight_scalar,
+                         int64_t n, int64_t chunk, double* partials_dev, void* stream);
+
+/* ---- VEGAS: replaces GridVolumes.random_bins/sample_indices (stratified_volume.py:
+ * 104-122), VegasMC.weights_at (vegas.py:68-72) and the loop body vegas.py:100-111 ---- */
+/* grid_dev: (ndim, 2K+1) = per axis [bounds(K+1) | sizes(K)].
+ * Samples points first_index..first_index+n-1 of iteration stream `stream_id`.
+ * Replay: idx_replay_dev (ndim, n) int64 + u_replay_dev (ndim, n) (reference layout).
+ * Optional outputs (reference layouts): x_dev (ndim, n), f_dev (n,), w_dev (n,),
+ * idx_dev (ndim, n) int64.  If dens->kind == HEPMC_NONE no integrand is evaluated and
+ * no partials are produced (two-kernel path: follow with hepmc_vegas_accumulate).
+ * Partials: stats_partials_dev (n_chunks,3) and hist_partials_dev (n_chunks, ndim*K),
+ * hist[d*K+k] = sum of f*w over the chunk's points with bin k on axis d. */
+int hepmc_vegas_sample(const hepmc_density_t* dens, const double* grid_dev, int ndim, int divisions,
+                       int64_t n, int64_t first_index, int64_t chunk, uint64_t seed, uint32_t stream_id,
+                       const int64_t* idx_replay_dev, const double* u_replay_dev,
+                       double* x_dev, double* f_dev, double* w_dev, int64_t* idx_dev,
+                       double* stats_partials_dev, double* hist_partials_dev, void* stream);
+
+/* Two-kernel path, second half: f_dev (n,) user integrand values, w_dev (n,), idx_dev
+ * (ndim, n) int64 -> the same partials as hepmc_vegas_sample. */
+int hepmc_vegas_accumulate(const double* f_dev, const double* w_dev, const int64_t* idx_dev,
+                           int ndim, int divisions, int64_t n, int64_t chunk,
+                           double* stats_partials_dev, double* hist_partials_dev, void* stream);
+
+/* Ordered column sums of hist partial rows [row_begin[s], row_begin[s+1]) -> out (n_out, ncols). */
+int hepmc_reduce_hist(const double* rows_dev, const int64_t* row_begin_host, int n_out, int ncols,
+                      double* out_dev, void* stream);
+
+/* Grid adaptation: replaces vegas.py:110-118 + damped_update (helper.py:56-72) + the
+ * sizes setter (stratified_volume.py:161-169, with bounds[d][0] = 0).
+ * slot_stats_dev (n_slots,3), slot_hist_dev (n_slots, ndim*K) are merged in slot order;
+ * est_var_dev[2*j], [2*j+1] receive est_j and var_j; grid_dev is updated in place. */
+int hepmc_vegas_update_grid(const double* slot_stats_dev, const double* slot_hist_dev, int n_slots,
+                            double* grid_dev, int ndim, int divisions, double c, int j,
+                            double* est_var_dev, void* stream);
+
+/* Workspace (bytes) hepmc_vegas_integrate needs for n points per iteration. */
+int64_t hepmc_vegas_workspace_bytes(int ndim, int divisions, int64_t n);
+/* Whole single-GPU VegasMC.__call__ (vegas.py:74-118): `iterations` x (sample, slot
+ * reduce, grid update) enqueued back to back, no host synchronisation.  est_var_dev
+ * (iterations, 2).  Iteration j uses stream id stream_id0 + j. */
+int hepmc_vegas_integrate(const hepmc_density_t* dens, double* grid_dev, int ndim, int divisions,
+                          int64_t n, int iterations, double c, uint64_t seed, uint32_t stream_id0,
+                          double* est_var_dev, void* workspace_dev, int64_t workspace_bytes,
+                          void* stream);
+
+/* GridVolumes.pdf (stratified_volume.py:74-83, default base counts): xs (n, ndim) -> (n,) */
+int hepmc_grid_pdf(const double* grid_dev, int ndim, int divisions, const double* xs_dev,
+                   int64_t n, double* out_dev, void* stream);
+
+/* ---- RAMBO: replaces phase_space.Rambo.map (rambo.py:38-69,162-173) ---------------- */
+/* out_dev (n, 4*nparticles) as [E,px,py,pz] per particle.  Native RNG (point index
+ * first_index + i) unless xs_replay_dev (n, 4*nparticles) is given. */
+int hepmc_rambo_map(int nparticles, double e_cm, int64_t n, int64_t first_index, uint64_t seed,
+                    uint32_t stream_id, const double* xs_replay_dev, double* out_dev, void* stream);
+/* Rambo.pdf (rambo.py:28-36): the constant 1/Phi_n, computed on the host. */
+double hepmc_rambo_pdf(int nparticles, double e_cm);
+
+/* ---- random-walk Metropolis ensembles: replaces MarkovUpdate.sample (base.py:44-97)
+ * + MetropolisUpdate.next_state/accept (metropolis.py:37-50,76-95) + DefaultMetropolis.
+ * proposal (:122-124) + proposals.Gaussian.proposal (gaussian.py:25-27), one chain per
+ * thread, diagonal proposal covariance -------------------------------------------------- */
+/* x0_dev (n_chains, ndim).  proposal_kind 0: Gaussian random walk, prop_scale_host[ndim] =
+ * sqrt(diag(cov)); proposal_kind 1: independence proposal uniform on (prop_scale_host[0],
+ * prop_scale_host[1])^ndim = DefaultMetropolis' default Uniform(ndim) (metropolis.py:114-115,
+ * uniform.py:33-34; the replay tape then holds uniforms).  sample_size T >= 1
+ * (chain[0] = x0, T-1 transitions).  Chain c has global index first_chain + c.
+ * Replay tapes: z_replay_dev (n_chains, T-1, ndim), u_replay_dev (n_chains, T-1).
+ * Outputs: chain_dev (n_chains, n_kept, ndim) with n_kept = ceil(T / thin), storing states
+ * t = 0, thin, 2*thin, ... (NULL = do not store); last_dev (n_chains, ndim); accepted_dev
+ * (n_chains,) int64 = number of transitions whose state changed (base.py:72-73);
+ * total_accepted_dev (1,) int64 is atomically incremented by the grid total. */
+int hepmc_rwm_chains(const hepmc_density_t* dens, const double* x0_dev, int proposal_kind,
+                     const double* prop_scale_host, int64_t n_chains, int64_t first_chain, int64_t sample_size, int64_t thin,
+                     uint64_t seed, uint32_t stream_id,
+                     const double* z_replay_dev, const double* u_replay_dev,
+                     double* chain_dev, double* last_dev, int64_t* accepted_dev,
+                     int64_t* total_accepted_dev, void* stream);
+
+/* ---- HMC ensembles: replaces HamiltonianUpdate (hmc.py:54-88), HamiltonLeapfrog
+ * (simulation.py:26-46), with the momentum distribution Gaussian(0, diag(mass)) ---------- */
+enum hepmc_grad_mode {
+    HEPMC_GRAD_EXACT = 0,     /* target density's own pot_gradient                         */
+    HEPMC_GRAD_ELM_GAUSS = 1, /* GaussianBasis surrogate (extreme_learning.py:222-230)      */
+    HEPMC_GRAD_ELM_TRIG = 2   /* TrigBasis surrogate (extreme_learning.py:140-146,253-257)  */
+};
+/* Extreme-learning-machine surrogate parameters (device pointers):
+ *   GAUSS: p0 = centers (nodes, ndim), p1 = widths (nodes,), out_w (nodes,)
+ *   TRIG : p0 = in_weights (nodes, ndim), p1 = biases (nodes,), out_w (nodes,) */
+typedef struct hepmc_elm {
+    int32_t mode;       /* hepmc_grad_mode */
+    int32_t nodes;
+    const double* p0_dev;
+    const double* p1_dev;
+    const double* out_w_dev;
+    double out_bias;
+} hepmc_elm_t;
+
+/* mass_host[ndim] = diag of the momentum covariance.  Momentum tape p_replay_dev
+ * (n_chains, T-1, ndim) holds the momenta themselves.  Other arguments as hepmc_rwm_chains.
+ * precision: 0 = float64 everywhere (parity mode); 1 = surrogate gradient in float32
+ * SIMT; 2 = surrogate gradient on tcgen05 tensor cores (TF32 operands, FP32 accumulate).
+ * The Metropolis test always uses the float64 target pdf, so 1 and 2 stay exact samplers. */
+int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int precision,
+                     const double* x0_dev, const double* mass_host, double step_size, int steps,
+                     int64_t n_chains, int64_t first_chain, int64_t sample_size, int64_t thin,
+                     uint64_t seed, uint32_t stream_id,
+                     const double* p_replay_dev, const double* u_replay_dev,
+                     double* chain_dev, double* last_dev, int64_t* accepted_dev,
+                     int64_t* total_accepted_dev, void* stream);
+
+/* ---- ELM surrogate: replaces FunctionBasis.eval (extreme_learning.py:18-29),
+ * RadialBasis.output_matrix/eval_gradient (:190-207,222-230), AdditiveBasis.* (:120-146) */
+/* xs_dev (n, ndim).  what: 0 = eval -> (n,), 1 = eval_gradient -> (n, ndim),
+ * 2 = output_matrix -> (n, nodes).  precision as in hepmc_hmc_chains. */
+int hepmc_elm_eval(const hepmc_elm_t* elm, int ndim, int what, int precision,
+                   const double* xs_dev, int64_t n, double* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEPMC_B200_H */

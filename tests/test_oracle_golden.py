@@ -186,9 +186,13 @@ def test_uniform_conventions():
     k = ((a.astype(np.uint64) >> np.uint64(12)) << np.uint64(32)) | b.astype(np.uint64)
     trick = (k | np.uint64(0x3FF0000000000000)).view(np.float64) - (1.0 - 2.0 ** -53)
     assert np.array_equal(trick, u)
+    wa = np.array([0, 0xffffffff, 0x80000000, 0x12345678], dtype=np.uint32)
+    wb = np.array([0, 0xffffffff, 0, 0x9abcdef0], dtype=np.uint32)
     for K in (1, 2, 15, 16, 50, 255):
-        bins, frac = O.vegas_bins_from_uniform(np.array([2.0 ** -53, 0.5, 1 - 2.0 ** -53]), K)
-        assert bins.max() <= K - 1 and bins.min() >= 0 and np.all((frac >= 0) & (frac < 1))
+        bins, frac = O.vegas_bin_frac(wa, wb, K)
+        assert bins.max() <= K - 1 and bins.min() >= 0 and np.all((frac > 0) & (frac < 1))
+        t = K * ((wa.astype(object) << 32) + wb.astype(object))      # exact big ints
+        assert [int(v) >> 64 for v in t] == list(bins)
 
 
 def test_ks_restatement():
