@@ -224,7 +224,8 @@ def test_vegas_gpu_count_invariance_at_abi_level():
         slots = torch.cat(rows, dim=0)
         assert slots.shape[0] == 8
         ev = torch.zeros(2, dtype=torch.float64, device=dev)
-        _lib.call("hepmc_vegas_update_grid", _lib.ptr(slots[:, :3].contiguous()), _lib.ptr(slots[:, 3:].contiguous()), 8,
+        s_stats, s_hist = slots[:, :3].contiguous(), slots[:, 3:].contiguous()   # keep alive across the launch
+        _lib.call("hepmc_vegas_update_grid", _lib.ptr(s_stats), _lib.ptr(s_hist), 8,
                   _lib.ptr(grid), ndim, K, 3.0, 0, _lib.ptr(ev), _lib.stream_ptr())
         results.append((slots.cpu().numpy(), grid.cpu().numpy(), ev.cpu().numpy()))
     for other in results[1:]:
