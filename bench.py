@@ -1,0 +1,338 @@
+"""Benchmark of the hepmc hot path on B200 (contract: one JSON line on rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Headline workload (BASELINE.json configs[2], the one the north-star target is quoted on):
+16-D camel VEGAS integration, divisions = 15, c = 3, 1e9 points per adaptation iteration
+for the whole job (strong scaling: the 1e9 points are sharded over the N GPUs by Philox
+counter range; one all-gather of the 8 slot partials per iteration).  A "step" is one
+VEGAS iteration = fused sample kernel + ordered slot reduction + grid update.
+
+  value   : points/s, device-timed (CUDA events, max over ranks), nothing memory-resident
+            is needed as input (counter-based RNG), the grid lives in HBM.
+  e2e     : the same metric through the public API `VegasMC(16, 15)(Camel(16), n, K)` from
+            host state: host->device copy of the grid, all launches, device->host read of the
+            per-iteration estimates; wall clock around the call.
+  roofline: dominant kernel vegas_sample_kernel, timed alone with CUDA events.
+  others  : RAMBO PS-points/s, banana RWM chain-steps/s, camel-8D HMC+ELM chain-steps/s.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_POINTS = 10 ** 9          # per VEGAS iteration, whole job
+NDIM, DIVISIONS, DAMPING = 16, 15, 3
+FLOP_PER_POINT = 12 * NDIM + 13          # 205 for n = 16
+METRIC = "camel-16D VEGAS points/s"
+
+
+# ------------------------------------------------------------------ reference arm / CPU baseline
+def _cpu_vegas_worker(args):
+    """One process = one independent VEGAS run of the NumPy port (the way the reference
+    parallelises: multiprocessing.Pool over independent seeds, src/make_sample.py:156-157)."""
+    seed, n, iters = args
+    from oracle import hepmc_oracle as O
+    rs = np.random.RandomState(seed)
+    t0 = time.perf_counter()
+    bounds = O.grid_uniform_bounds(NDIM, DIVISIONS)
+    for j in range(iters):
+        idx = np.stack([rs.randint(0, DIVISIONS, n) for _ in range(NDIM)])      # stratified_volume.py:110-111
+        u = np.stack([rs.rand(n) for _ in range(NDIM)])                         # :119-121
+        _, _, bounds, _ = O.vegas_iteration(O.camel_pdf, bounds, idx, u, DAMPING, j)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(n_per_step, steps, procs):
+    import multiprocessing as mp
+    if procs == 1:
+        dt = _cpu_vegas_worker((1234, n_per_step, steps))
+    else:
+        ctx = mp.get_context("fork")
+        t0 = time.perf_counter()
+        with ctx.Pool(procs) as pool:
+            pool.map(_cpu_vegas_worker, [(1234 + i, n_per_step, steps) for i in range(procs)])
+        dt = time.perf_counter() - t0
+    return procs * n_per_step * steps / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    n_step = 200_000                      # bounded sample of the same workload per step and process
+    cpu_baseline(n_step, 1, procs)        # warm-up (imports, page-in)
+    value, dt = cpu_baseline(n_step, args.steps, procs)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "camel-16D VEGAS, divisions=15, c=3 (BASELINE.json configs[2])",
+                   "points_per_step_per_process": n_step, "processes": procs},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": procs, "kind": "port",
+                         "sample": "%d processes x %d iterations x %d points of the NumPy port of "
+                                   "VegasMC(16,15)(Camel(16)) (oracle/hepmc_oracle.py); the reference is pure "
+                                   "Python and /root/reference does not exist on the GPU box" % (procs, args.steps, n_step)},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------ our arm
+def run_b200(args):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import hepmc_b200 as H
+    from hepmc_b200 import _lib, parallel, rng
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    H.set_outputs("torch")
+    dev = torch.device("cuda", local_rank)
+    steps, warmup = args.steps, max(args.warmup, 0)
+    n = args.points
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    camel = H.densities.Camel(NDIM)
+    mc = H.VegasMC(NDIM, divisions=DIVISIONS, c=DAMPING)
+    H.seed(1234)
+    if warmup:
+        mc(camel, n, warmup, keep_samples=False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    res = mc(camel, n, steps, apriori=False, keep_samples=False)   # exactly K steps, one sync at its end
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = n * steps / (ms_total * 1e-3)
+
+    # ---- e2e: public API from host state, wall clock, includes H2D of the grid + D2H of results
+    barrier()
+    t0 = time.perf_counter()
+    mc_e2e = H.VegasMC(NDIM, divisions=DIVISIONS, c=DAMPING)
+    r_e2e = mc_e2e(camel, n, steps, keep_samples=False)
+    integral_host = float(r_e2e.integral)
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = n * steps / float(dt.item())
+    grid_bytes = NDIM * (2 * DIVISIONS + 1) * 8
+
+    # ---- roofline of the dominant kernel: vegas_sample_kernel alone, CUDA events on its stream
+    chunk = _lib.default_chunk(n)
+    first, n_local, begins = parallel.local_span(n, chunk)
+    nc = max(begins[-1], 1)
+    sp = torch.zeros((nc, 3), dtype=torch.float64, device=dev)
+    hp = torch.zeros((nc, NDIM * DIVISIONS), dtype=torch.float64, device=dev)
+    blk = camel._block()
+    grid = mc.volumes.device_grid()
+    kms = []
+    for i in range(3 + min(steps, 5)):
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        _lib.call("hepmc_vegas_sample", ctypes.byref(blk), _lib.ptr(grid), NDIM, DIVISIONS, n_local, first, chunk,
+                  1234, 1000 + i, None, None, None, None, None, None, _lib.ptr(sp), _lib.ptr(hp), _lib.stream_ptr())
+        k1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            kms.append(k0.elapsed_time(k1))
+    kernel_ms = float(np.mean(kms))
+    fp64_peak = _lib.fp64_probe(1 << 15) / 1e12          # measured DFMA TFLOP/s on this GPU, live
+    achieved = FLOP_PER_POINT * n_local / (kernel_ms * 1e-3) / 1e12
+
+    others = {}
+    if rank == 0 and not args.no_others:
+        others = other_workloads(H, _lib, torch, fp64_peak)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, cdt = cpu_baseline(1_000_000, 2, 1)
+        cpu = {"value": v, "unit": "points/s", "cores": 1, "kind": "port",
+               "sample": "2 iterations x 1e6 points of the NumPy port of VegasMC(16,15)(Camel(16)) "
+                         "(oracle/hepmc_oracle.py), single process, %.1f s" % cdt}
+    line = {
+        "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "camel-16D VEGAS, divisions=15, c=3, %.3g points/iteration whole job "
+                               "(BASELINE.json configs[2]); keep_samples=False" % n,
+                   "parallelism": "philox-counter sharding x%d, all-gather of 8 slot partials per iteration" % world,
+                   "l2": "no memory-resident input (counter RNG in registers); partial rows are written, never re-read hot",
+                   "integral": res.integral, "integral_err": res.integral_err},
+        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": grid_bytes / steps,
+                "d2h_bytes_per_step": 16, "integral": integral_host},
+        "gpu_launches": 4 * steps,
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "fp64_simt", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp64_peak, "traffic": None,
+                     "kernel": "vegas_sample_kernel", "kernel_ms": kernel_ms, "points_per_launch": n_local,
+                     "flop_per_point": FLOP_PER_POINT,
+                     "peak_source": "live DFMA probe (hepmc_fp64_probe); MEASURED_PEAKS.json has no FP64 entry "
+                                    "(hbm_gbs=%s)" % peaks.get("hbm_gbs"),
+                     "kernel_share_of_step": kernel_ms / (ms_total / steps)},
+        "cpu_baseline": cpu,
+        "others": others,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def other_workloads(H, _lib, torch, fp64_peak):
+    """The other two metrics BASELINE.json names, single GPU, device-timed."""
+    out = {}
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e-3)
+        return float(np.mean(ts))
+    hbm = None
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        hbm = 6650.0
+    # RAMBO 2->4, sqrt(s) = 100 GeV: 2^27 points per launch (16 GiB of output, larger than L2)
+    m = H.phase_space.Rambo(100., 4)
+    nr = 1 << 27
+    buf = torch.empty((nr, 16), dtype=torch.float64, device="cuda")
+    t = timed(lambda: m.generate(nr, out=buf))
+    del buf
+    out["rambo"] = {"metric": "RAMBO 2->4 PS-points/s", "value": nr / t, "points": nr,
+                    "roofline": {"bound": "hbm", "achieved": nr * 128 / t / 1e9, "peak": hbm, "unit": "GB/s",
+                                 "frac": nr * 128 / t / 1e9 / hbm, "bytes_per_point": 128}}
+    # banana 2-D RWM: 1e6 chains x 1e3 steps per launch (the 1e4-step config is 10 such launches)
+    C, T = 1_000_000, 1001
+    met = H.DefaultMetropolis(2, H.densities.Banana(2), H.proposals.Gaussian(2, cov=10 * np.eye(2)))
+    x0 = torch.tensor([[0., 10.]], device="cuda", dtype=torch.float64).repeat(C, 1)
+    t = timed(lambda: met.sample(T, x0, store_chain=False))
+    out["rwm"] = {"metric": "banana-2D RWM chain-steps/s", "value": C * (T - 1) / t, "chains": C, "steps": T - 1,
+                  "roofline": {"bound": "fp64_simt", "achieved": 23 * C * (T - 1) / t / 1e12, "peak": fp64_peak,
+                               "unit": "TFLOP/s", "frac": 23 * C * (T - 1) / t / 1e12 / fp64_peak, "flop_per_step": 23}}
+    # camel-8D HMC, ELM Gaussian-basis surrogate gradient, 1e5 chains x 20 leapfrog
+    rs = np.random.default_rng(0)
+    for nodes in (100, 1024):
+        basis = H.surrogate.GaussianBasis(8)
+        params = (rs.random((nodes, 8)), 0.01 + 0.99 * rs.random(nodes), None)
+        w = 0.01 * rs.standard_normal(nodes)
+        for prec in ("f64", "f32"):
+            tgt = H.densities.Camel(8)
+            H.surrogate.attach_surrogate_gradient(tgt, basis, params, 0.0, w)
+            upd = H.hamiltonian.HamiltonianUpdate(tgt, H.densities.Gaussian(8), 20, 0.01, precision=prec)
+            Ch, Th = 100_000, 3
+            x0h = torch.full((Ch, 8), 1 / 3, device="cuda", dtype=torch.float64)
+            t = timed(lambda: upd.sample(Th, x0h, store_chain=False), reps=2)
+            flop = 21 * (4 * nodes * 8 + 5 * nodes + 4 * 8) + 20 * 64 + 72 + 48
+            out["hmc_elm%d_%s" % (nodes, prec)] = {
+                "metric": "camel-8D HMC+ELM chain-steps/s", "value": Ch * (Th - 1) / t, "nodes": nodes,
+                "achieved_tflops": flop * Ch * (Th - 1) / t / 1e12}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=float, default=N_POINTS)
+    ap.add_argument("--no-others", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.points = int(args.points)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

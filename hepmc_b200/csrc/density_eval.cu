@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) density_eval_kernel(const __grid_constant
         } else {  // HEPMC_PDF_GRADIENT
             double* g = out + i * nd;
             if (dens.kind == HEPMC_CAMEL || dens.kind == HEPMC_UCAMEL) {
-                const CamelModes m = camel_modes(dens, x);
+                const CamelModes m = camel_modes(dens, x, nd);
                 const bool inside = (dens.kind == HEPMC_UCAMEL) || m.inside;
                 for (int d = 0; d < nd; ++d)
                     g[d] = inside ? ((-x[d] + dens.a[d]) / dens.s2 * m.na + (-x[d] + dens.b[d]) / dens.s2 * m.nb) / 2.0

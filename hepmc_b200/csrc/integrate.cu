@@ -11,188 +11,9 @@
 // L owns axis d = L % ndim and a PRIVATE column hist[k][L] in shared memory, and walks the
 // tile's points in fixed order (plain LDS/DADD/STS, conflict-free banks).  The per-lane
 // columns are summed in fixed order when the chunk ends.
-#include "density.cuh"
+#include "integrate_kernels.cuh"
 
 namespace hepmc {
-
-constexpr int kBinWords = HEPMC_MAX_DIM / 4 + 1;  // packed bin bytes per point, padded (bank-conflict-free)
-
-struct SampleArgs {
-    const double* grid;  // VEGAS: (ndim, 2K+1); plain: unused
-    int ndim, K;
-    int64_t n, first_index, chunk;
-    uint64_t seed;
-    uint32_t stream_id;
-    const int64_t* idx_replay;
-    const double* u_replay;
-    double* x_out;
-    double* f_out;
-    double* w_out;
-    int64_t* idx_out;
-    double* stats_partials;
-    double* hist_partials;
-    double kpow;
-    // two-kernel path inputs (accumulate)
-    const double* f_in;
-    const double* w_in;
-    const int64_t* idx_in;
-};
-
-// lane L < ngrp*ndim: axis d = L % ndim, walks points grp, grp+ngrp, ... of the warp tile.
-__device__ __forceinline__ void warp_hist_update(double* hist_w, const double* wf_w, const uint32_t* bins_w,
-                                                 int ndim, int lane) {
-    const int ngrp = 32 / ndim;
-    if (lane < ngrp * ndim) {
-        const int d = lane % ndim, grp = lane / ndim;
-        const int word = d >> 2, shift = 8 * (d & 3);
-        for (int p = grp; p < 32; p += ngrp) {
-            const double v = wf_w[p];
-            const uint32_t bin = (bins_w[p * kBinWords + word] >> shift) & 0xffu;
-            hist_w[bin * 32 + lane] += v;
-        }
-    }
-}
-
-__device__ __forceinline__ void block_hist_flush(const double* s_hist, int ndim, int K, int nwarps,
-                                                 double* out_row) {
-    const int ngrp = 32 / ndim;
-    for (int j = threadIdx.x; j < ndim * K; j += blockDim.x) {
-        const int d = j / K, k = j % K;
-        double s = 0.0;
-        for (int w = 0; w < nwarps; ++w)
-            for (int g = 0; g < ngrp; ++g) s += s_hist[(w * K + k) * 32 + g * ndim + d];
-        out_row[j] = s;
-    }
-}
-
-struct SmemLayout {
-    double* grid;
-    Stats* stats;
-    double* hist;
-    double* wf;
-    uint32_t* bins;
-};
-
-__host__ __device__ inline size_t vegas_smem_bytes(int ndim, int K, int threads) {
-    const int nw = threads / 32;
-    size_t b = (size_t)ndim * (2 * K + 1) * 8;  // grid
-    b += 32 * sizeof(Stats);                    // block merge scratch
-    b += (size_t)nw * K * 32 * 8;               // private histogram columns
-    b += (size_t)nw * 32 * 8;                   // wf tile
-    b += (size_t)nw * 32 * kBinWords * 4;       // packed bins tile
-    return b;
-}
-
-__device__ __forceinline__ SmemLayout carve(double* base, int ndim, int K, int nw) {
-    SmemLayout s;
-    s.grid = base;
-    s.stats = reinterpret_cast<Stats*>(s.grid + (size_t)ndim * (2 * K + 1));
-    s.hist = reinterpret_cast<double*>(s.stats + 32);
-    s.wf = s.hist + (size_t)nw * K * 32;
-    s.bins = reinterpret_cast<uint32_t*>(s.wf + nw * 32);
-    return s;
-}
-
-// ------------------------------------------------------------------ VEGAS sample (+ fused integrand)
-__global__ void __launch_bounds__(256) vegas_sample_kernel(const __grid_constant__ Dens dens,
-                                                           const __grid_constant__ SampleArgs a) {
-    extern __shared__ double smem_raw[];
-    const int ndim = a.ndim, K = a.K;
-    const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const SmemLayout s = carve(smem_raw, ndim, K, nw);
-    const bool fused = dens.kind != HEPMC_NONE;
-
-    for (int i = threadIdx.x; i < ndim * (2 * K + 1); i += blockDim.x) s.grid[i] = a.grid[i];
-    if (fused)
-        for (int i = threadIdx.x; i < nw * K * 32; i += blockDim.x) s.hist[i] = 0.0;
-    __syncthreads();
-
-    double* hist_w = s.hist + (size_t)warp * K * 32;
-    double* wf_w = s.wf + warp * 32;
-    uint32_t* bins_w = s.bins + warp * 32 * kBinWords;
-
-    const PhiloxKey key = philox_expand(a.seed);
-    const bool replay = a.u_replay != nullptr;
-    const int64_t chunk0 = (int64_t)blockIdx.x * a.chunk;
-    const int ppt = (int)(a.chunk / blockDim.x);
-    const int ncalls = (ndim + 1) >> 1;
-    const int stride = 2 * K + 1;
-    ShiftedAcc acc;
-    acc.init();
-
-    for (int it = 0; it < ppt; ++it) {
-        const int64_t li = chunk0 + (int64_t)it * blockDim.x + threadIdx.x;
-        const bool valid = li < a.n;
-        double wf = 0.0;
-        uint32_t packed[kBinWords - 1];
-#pragma unroll
-        for (int q = 0; q < kBinWords - 1; ++q) packed[q] = 0u;
-        if (valid) {
-            const uint64_t g = (uint64_t)(a.first_index + li);
-            PdfAcc pa;
-            pa.init();
-            double w = 1.0;
-            for (int call = 0; call < ncalls; ++call) {
-                U4 r{0u, 0u, 0u, 0u};
-                if (!replay) r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)call, a.stream_id, key);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int d = 2 * call + h;
-                    if (d < ndim) {
-                        uint32_t bin;
-                        double frac;
-                        if (replay) {
-                            bin = (uint32_t)a.idx_replay[(int64_t)d * a.n + li];
-                            frac = a.u_replay[(int64_t)d * a.n + li];
-                        } else {
-                            bin_frac(h ? r.z : r.x, h ? r.w : r.y, (uint32_t)K, bin, frac);
-                        }
-                        const double* gd = s.grid + d * stride;
-                        const double sz = gd[K + 1 + bin];
-                        const double x = gd[bin] + sz * frac;  // stratified_volume.py:119-121
-                        w *= sz;                               // vegas.py:69-70
-                        if (fused) pdf_acc_dim(dens, pa, d, x);
-#pragma unroll
-                        for (int q = 0; q < kBinWords - 1; ++q)
-                            if (q == (d >> 2)) packed[q] |= bin << (8 * (d & 3));
-                        if (a.x_out) a.x_out[(int64_t)d * a.n + li] = x;
-                        if (a.idx_out) a.idx_out[(int64_t)d * a.n + li] = (int64_t)bin;
-                    }
-                }
-            }
-            w *= a.kpow;  // vegas.py:72 (partition_count evaluated in floating point, App. B1)
-            if (a.w_out) a.w_out[li] = w;
-            if (fused) {
-                const double f = pdf_acc_finish(dens, pa);
-                wf = f * w;  // vegas.py:104
-                acc.add(wf);
-                if (a.f_out) a.f_out[li] = f;
-            }
-        }
-        if (fused) {
-            wf_w[lane] = wf;
-#pragma unroll
-            for (int q = 0; q < kBinWords - 1; ++q)
-                if (q * 4 < ndim) bins_w[lane * kBinWords + q] = packed[q];
-            __syncwarp();
-            warp_hist_update(hist_w, wf_w, bins_w, ndim, lane);
-            __syncwarp();
-        }
-    }
-    if (!fused) return;
-    __syncthreads();
-    block_hist_flush(s.hist, ndim, K, nw, a.hist_partials + (size_t)blockIdx.x * ndim * K);
-    // per-thread -> warp -> block (fixed order)
-    Stats st = warp_merge(acc.stats());
-    if (lane == 0) s.stats[warp] = st;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        Stats r{0.0, 0.0, 0.0};
-        for (int w = 0; w < nw; ++w) r = merge(r, s.stats[w]);
-        double* o = a.stats_partials + (size_t)blockIdx.x * 3;
-        o[0] = r.n; o[1] = r.mean; o[2] = r.m2;
-    }
-}
 
 // ------------------------------------------------------------------ two-kernel path: accumulate
 __global__ void __launch_bounds__(256) vegas_accumulate_kernel(const __grid_constant__ SampleArgs a) {
@@ -237,57 +58,6 @@ __global__ void __launch_bounds__(256) vegas_accumulate_kernel(const __grid_cons
     if (threadIdx.x == 0) {
         Stats r{0.0, 0.0, 0.0};
         for (int w = 0; w < nw; ++w) r = merge(r, s.stats[w]);
-        double* o = a.stats_partials + (size_t)blockIdx.x * 3;
-        o[0] = r.n; o[1] = r.mean; o[2] = r.m2;
-    }
-}
-
-// ------------------------------------------------------------------ plain MC
-__global__ void __launch_bounds__(256) plain_sample_kernel(const __grid_constant__ Dens dens,
-                                                           const __grid_constant__ SampleArgs a) {
-    __shared__ Stats s_stats[8];
-    const int ndim = a.ndim;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool fused = dens.kind != HEPMC_NONE;
-    const PhiloxKey key = philox_expand(a.seed);
-    const bool replay = a.u_replay != nullptr;
-    const int64_t chunk0 = (int64_t)blockIdx.x * a.chunk;
-    const int ppt = (int)(a.chunk / blockDim.x);
-    const int ncalls = (ndim + 1) >> 1;
-    ShiftedAcc acc;
-    acc.init();
-    for (int it = 0; it < ppt; ++it) {
-        const int64_t li = chunk0 + (int64_t)it * blockDim.x + threadIdx.x;
-        if (li >= a.n) break;
-        const uint64_t g = (uint64_t)(a.first_index + li);
-        PdfAcc pa;
-        pa.init();
-        for (int call = 0; call < ncalls; ++call) {
-            U4 r{0u, 0u, 0u, 0u};
-            if (!replay) r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)call, a.stream_id, key);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int d = 2 * call + h;
-                if (d < ndim) {
-                    const double x = replay ? a.u_replay[li * ndim + d] : u52(h ? r.z : r.x, h ? r.w : r.y);
-                    if (fused) pdf_acc_dim(dens, pa, d, x);
-                    if (a.x_out) a.x_out[li * ndim + d] = x;  // (N, ndim) row-major, integration.py:45
-                }
-            }
-        }
-        if (fused) {
-            const double f = pdf_acc_finish(dens, pa);
-            acc.add(f);
-            if (a.f_out) a.f_out[li] = f;
-        }
-    }
-    if (!fused) return;
-    Stats st = warp_merge(acc.stats());
-    if (lane == 0) s_stats[warp] = st;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        Stats r{0.0, 0.0, 0.0};
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = merge(r, s_stats[w]);
         double* o = a.stats_partials + (size_t)blockIdx.x * 3;
         o[0] = r.n; o[1] = r.mean; o[2] = r.m2;
     }
@@ -494,6 +264,47 @@ static int check_sample_common(const char* who, int ndim, int K, int64_t n, int6
     return 0;
 }
 
+#define HEPMC_GENERIC_CASE(KIND)                                                                            \
+    case KIND:                                                                                              \
+        if (vegas) {                                                                                        \
+            HEPMC_CUDA(cudaFuncSetAttribute(vegas_sample_kernel<KIND, 0, false>,                            \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+            vegas_sample_kernel<KIND, 0, false><<<blocks, threads, smem, st>>>(dens, a);                    \
+        } else {                                                                                            \
+            plain_sample_kernel<KIND, 0, false><<<blocks, 256, 0, st>>>(dens, a);                           \
+        }                                                                                                   \
+        break;
+
+// fast = native RNG and no per-point outputs: compile-time (kind, ndim) instance when one
+// exists (ndim <= 16), else the generic kernel (runtime ndim and flags).
+static int launch_sample(bool vegas, bool fast, const Dens& dens, const SampleArgs& a, unsigned blocks, int threads,
+                         size_t smem, cudaStream_t st) {
+    if (fast) {
+        int e = -100;
+        switch (dens.kind) {
+            case HEPMC_CAMEL: e = launch_fast_camel(vegas, a.ndim, dens, a, blocks, threads, smem, st); break;
+            case HEPMC_UCAMEL: e = launch_fast_ucamel(vegas, a.ndim, dens, a, blocks, threads, smem, st); break;
+            case HEPMC_BANANA: e = launch_fast_banana(vegas, a.ndim, dens, a, blocks, threads, smem, st); break;
+            case HEPMC_GAUSSIAN: e = launch_fast_gaussian(vegas, a.ndim, dens, a, blocks, threads, smem, st); break;
+            case HEPMC_UNIFORM: e = launch_fast_uniform(vegas, a.ndim, dens, a, blocks, threads, smem, st); break;
+            default: break;
+        }
+        if (e != -100) return e;
+    }
+    switch (dens.kind) {
+        HEPMC_GENERIC_CASE(HEPMC_CAMEL)
+        HEPMC_GENERIC_CASE(HEPMC_UCAMEL)
+        HEPMC_GENERIC_CASE(HEPMC_BANANA)
+        HEPMC_GENERIC_CASE(HEPMC_GAUSSIAN)
+        HEPMC_GENERIC_CASE(HEPMC_UNIFORM)
+        HEPMC_GENERIC_CASE(HEPMC_NONE)
+        default:
+            set_error("unknown density kind %d", dens.kind);
+            return HEPMC_E_ARG;
+    }
+    return 0;
+}
+
 }  // namespace hepmc
 
 using namespace hepmc;
@@ -522,7 +333,9 @@ int hepmc_plain_mc_sample(const hepmc_density_t* dens, int64_t n, int64_t first_
     a.seed = seed; a.stream_id = stream_id; a.u_replay = u_replay_dev;
     a.x_out = data_dev; a.f_out = f_dev; a.stats_partials = partials_dev;
     const int64_t blocks = (n + chunk - 1) / chunk;
-    plain_sample_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(*dens, a);
+    const bool fast = dens->kind != HEPMC_NONE && !u_replay_dev && !data_dev && !f_dev;
+    int e2 = launch_sample(false, fast, *dens, a, (unsigned)blocks, 256, 0, as_stream(stream));
+    if (e2) return e2;
     HEPMC_LAUNCH_CHECK();
     return 0;
 }
@@ -586,7 +399,6 @@ int hepmc_vegas_sample(const hepmc_density_t* dens, const double* grid_dev, int 
     HEPMC_REQUIRE(threads > 0, HEPMC_E_UNSUPPORTED, "hepmc_vegas_sample: grid %d x %d does not fit shared memory", ndim,
                   divisions);
     HEPMC_REQUIRE(chunk % threads == 0, HEPMC_E_ARG, "chunk not a multiple of the block size");
-    HEPMC_CUDA(cudaFuncSetAttribute(vegas_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SampleArgs a{};
     a.grid = grid_dev; a.ndim = ndim; a.K = divisions; a.n = n; a.first_index = first_index; a.chunk = chunk;
     a.seed = seed; a.stream_id = stream_id; a.idx_replay = idx_replay_dev; a.u_replay = u_replay_dev;
@@ -594,7 +406,9 @@ int hepmc_vegas_sample(const hepmc_density_t* dens, const double* grid_dev, int 
     a.stats_partials = stats_partials_dev; a.hist_partials = hist_partials_dev;
     a.kpow = pow((double)divisions, (double)ndim);
     const int64_t blocks = (n + chunk - 1) / chunk;
-    vegas_sample_kernel<<<(unsigned)blocks, threads, smem, as_stream(stream)>>>(*dens, a);
+    const bool fast = fused && !u_replay_dev && !x_dev && !f_dev && !w_dev && !idx_dev;
+    int e2 = launch_sample(true, fast, *dens, a, (unsigned)blocks, threads, smem, as_stream(stream));
+    if (e2) return e2;
     HEPMC_LAUNCH_CHECK();
     return 0;
 }

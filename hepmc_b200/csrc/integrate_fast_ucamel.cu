@@ -1,0 +1,7 @@
+// Throughput instances of the fused plain-MC / VEGAS kernels for the ucamel integrand:
+// compile-time dimensionality 1..16, native Philox draws, no per-point outputs.
+#include "integrate_kernels.cuh"
+
+namespace hepmc {
+HEPMC_DEFINE_FAST_LAUNCHER(launch_fast_ucamel, HEPMC_UCAMEL)
+}  // namespace hepmc
