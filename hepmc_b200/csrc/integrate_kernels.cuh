@@ -112,7 +112,7 @@ __device__ __forceinline__ SmemLayout carve(double* base, int ndim, int K, int n
 //       x / f / w / idx outputs are honoured through warp-uniform runtime flags.
 // Shared grid layout: per axis K entries of (bound_k, size_k) as double2 -> one LDS.128.
 template <int KIND, int NDIM_T, bool FAST>
-__global__ void __launch_bounds__(256) vegas_sample_kernel(const __grid_constant__ Dens dens,
+__global__ void __launch_bounds__(256, FAST ? 3 : 1) vegas_sample_kernel(const __grid_constant__ Dens dens,
                                                            const __grid_constant__ SampleArgs a) {
     extern __shared__ double smem_raw[];
     const int ndim = NDIM_T ? NDIM_T : a.ndim;
@@ -319,6 +319,8 @@ int launch_fast_uniform(bool, int, const Dens&, const SampleArgs&, unsigned, int
         if (vegas) {                                                                                        \
             HEPMC_CUDA(cudaFuncSetAttribute(vegas_sample_kernel<KIND, ND, true>,                            \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+            HEPMC_CUDA(cudaFuncSetAttribute(vegas_sample_kernel<KIND, ND, true>,                            \
+                                            cudaFuncAttributePreferredSharedMemoryCarveout, 100));          \
             vegas_sample_kernel<KIND, ND, true><<<blocks, threads, smem, st>>>(dens, a);                    \
         } else {                                                                                            \
             plain_sample_kernel<KIND, ND, true><<<blocks, 256, 0, st>>>(dens, a);                           \
