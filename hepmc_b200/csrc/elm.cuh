@@ -44,15 +44,21 @@ __device__ __forceinline__ void elm_gradient(int mode, int nodes, const T* __res
 #pragma unroll
     for (int k = 0; k < NDIM; ++k) { xt[k] = (T)x[k]; acc[k] = (T)0; }
     if (mode == HEPMC_GRAD_ELM_GAUSS) {
+        // float64: two nodes in flight and split square sums (the FP64 pipe is latency bound at
+        // the occupancy 168 registers allow); float32: plain loop (issue bound, measured faster)
+        constexpr int UNR = sizeof(T) == 8 ? 2 : 1;
+#pragma unroll UNR
         for (int i = 0; i < nodes; ++i) {
             const T* r = tab + i * row;
             T diff[NDIM];
-            T ss = (T)0;
+            T ss0 = (T)0, ss1 = (T)0;
 #pragma unroll
             for (int k = 0; k < NDIM; ++k) {
                 diff[k] = xt[k] - r[k];
-                ss = fma(diff[k], diff[k], ss);
+                if (sizeof(T) == 8 && (k & 1)) ss1 = fma(diff[k], diff[k], ss1);
+                else ss0 = fma(diff[k], diff[k], ss0);
             }
+            const T ss = sizeof(T) == 8 ? ss0 + ss1 : ss0;
             const T gi = -elm_exp(-(ss * r[NDIM])) * r[NDIM + 1];  // basis_function_gradient * ow/w^2
 #pragma unroll
             for (int k = 0; k < NDIM; ++k) acc[k] = fma(gi, diff[k], acc[k]);

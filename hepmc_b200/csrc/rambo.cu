@@ -58,11 +58,12 @@ __global__ void __launch_bounds__(128) rambo_kernel(const __grid_constant__ Ramb
             rambo_q(u0, u1, u2, u3, q[p]);
             Q0 += q[p][0]; Q1 += q[p][1]; Q2 += q[p][2]; Q3 += q[p][3];  // rambo.py:46
         }
-        const double M = sqrt(((Q0 * Q0 - Q1 * Q1) - Q2 * Q2) - Q3 * Q3);  // rambo.py:48
-        const double b1 = -Q1 / M, b2 = -Q2 / M, b3 = -Q3 / M;             // :49
-        const double x = a.e_cm / M;                                      // :50
-        const double gamma = Q0 / M;                                      // :51
-        const double aa = 1.0 / (1.0 + gamma);                            // :52
+        // 1/M once (rsqrt, <= 1 ulp) instead of sqrt + five divisions: rambo.py:48-52
+        const double invM = rsqrt(((Q0 * Q0 - Q1 * Q1) - Q2 * Q2) - Q3 * Q3);
+        const double b1 = -Q1 * invM, b2 = -Q2 * invM, b3 = -Q3 * invM;
+        const double x = a.e_cm * invM;
+        const double gamma = Q0 * invM;
+        const double aa = 1.0 / (1.0 + gamma);
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             const double bdotq = (b1 * q[p][1] + b2 * q[p][2]) + b3 * q[p][3];  // :54
@@ -97,10 +98,10 @@ __global__ void __launch_bounds__(128) rambo_kernel_generic(const __grid_constan
             Q0 += q[0]; Q1 += q[1]; Q2 += q[2]; Q3 += q[3];
             st256(a.out + (i * np + p) * 4, q[0], q[1], q[2], q[3]);
         }
-        const double M = sqrt(((Q0 * Q0 - Q1 * Q1) - Q2 * Q2) - Q3 * Q3);
-        const double b1 = -Q1 / M, b2 = -Q2 / M, b3 = -Q3 / M;
-        const double x = a.e_cm / M;
-        const double gamma = Q0 / M;
+        const double invM = rsqrt(((Q0 * Q0 - Q1 * Q1) - Q2 * Q2) - Q3 * Q3);
+        const double b1 = -Q1 * invM, b2 = -Q2 * invM, b3 = -Q3 * invM;
+        const double x = a.e_cm * invM;
+        const double gamma = Q0 * invM;
         const double aa = 1.0 / (1.0 + gamma);
         for (int p = 0; p < np; ++p) {
             double* o = a.out + (i * np + p) * 4;
