@@ -5,54 +5,9 @@
 // State (x, pdf, counters) lives in registers; randomness is Philox4x32-10 keyed by the
 // GLOBAL chain index and the step, so any split of the chain range over GPUs reproduces
 // the same chains.  Acceptance counts: per chain + warp-shuffle reduced grid total.
-#include "density.cuh"
-#include "elm.cuh"
+#include "chains.cuh"
 
 namespace hepmc {
-
-struct ChainArgs {
-    const double* x0;
-    int64_t n_chains, first_chain, T, thin, n_kept;
-    uint64_t seed;
-    uint32_t stream_id;
-    const double* z_replay;  // rwm: normals (C, T-1, nd); hmc: momenta (C, T-1, nd)
-    const double* u_replay;  // (C, T-1)
-    double* chain;           // (C, n_kept, nd) or NULL
-    double* last;            // (C, nd)
-    int64_t* accepted;       // (C,)
-    unsigned long long* total_accepted;
-    double scale[HEPMC_MAX_CHAIN_DIM];  // rwm: sqrt(diag cov); hmc: sqrt(mass)
-    int prop_kind;                      // rwm: 0 = Gaussian random walk, 1 = uniform independence on (lo, hi)
-    double prop_lo, prop_hi;
-    // hmc
-    double step_size;
-    int steps;
-    int precision;
-};
-
-// two standard normals from one Philox call (Box-Muller on two 52-bit uniforms)
-__device__ __forceinline__ void normal_pair(const U4& r, double& z0, double& z1) {
-    const double u1 = u52(r.x, r.y), u2 = u52(r.z, r.w);
-    const double rad = sqrt(-2.0 * log(u1));
-    double sn, cs;
-    sincospi(2.0 * u2, &sn, &cs);
-    z0 = rad * cs;
-    z1 = rad * sn;
-}
-
-template <int NDIM>
-__device__ __forceinline__ void store_state(double* chain, int64_t c, int64_t n_kept, int64_t slot,
-                                            const double (&x)[NDIM]) {
-    double* o = chain + ((size_t)c * n_kept + slot) * NDIM;
-#pragma unroll
-    for (int d = 0; d < NDIM; ++d) o[d] = x[d];
-}
-
-__device__ __forceinline__ void finish_counts(const ChainArgs& a, bool active, int64_t c, int64_t acc) {
-    if (active && a.accepted) a.accepted[c] = acc;
-    const int64_t tot = warp_sum_i64(active ? acc : 0);
-    if ((threadIdx.x & 31) == 0 && a.total_accepted && tot) atomicAdd(a.total_accepted, (unsigned long long)tot);
-}
 
 // ------------------------------------------------------------------ random-walk Metropolis
 // base.py:56-97, metropolis.py:76-95,122-124, proposals/gaussian.py:25-27
@@ -294,8 +249,6 @@ int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int pr
                   "hepmc_hmc_chains: target must be a built-in density (kind %d)", dens->kind);
     HEPMC_REQUIRE(steps >= 0, HEPMC_E_ARG, "hepmc_hmc_chains: steps < 0");
     HEPMC_REQUIRE(precision >= 0 && precision <= 2, HEPMC_E_ARG, "hepmc_hmc_chains: precision must be 0, 1 or 2");
-    HEPMC_REQUIRE(precision != 2, HEPMC_E_UNSUPPORTED,
-                  "hepmc_hmc_chains: tensor-core surrogate (precision 2) is served by hepmc_hmc_chains_tc");
     const int nd = dens->ndim;
     ChainArgs a{};
     int e = fill_chain_args(a, "hepmc_hmc_chains", nd, x0_dev, mass_host, nd, true, n_chains, first_chain, sample_size, thin,
@@ -326,9 +279,15 @@ int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int pr
     }
     pd.s1 = nd * log(2.0 * 3.141592653589793) + logdet;
     if (n_chains == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    if (precision == 2 && el.mode != HEPMC_GRAD_EXACT) {
+        HEPMC_REQUIRE(el.mode == HEPMC_GRAD_ELM_GAUSS, HEPMC_E_UNSUPPORTED,
+                      "hepmc_hmc_chains: the tensor-core path implements the Gaussian basis");
+        return launch_hmc_tc(*dens, pd, el, a, st);
+    }
+    if (precision == 2) precision = 0;  // exact gradient: nothing to put on tensor cores
     const int threads = 128;
     const unsigned blocks = (unsigned)((n_chains + threads - 1) / threads);
-    cudaStream_t st = as_stream(stream);
     int dev = 0, maxs = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&maxs, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);

@@ -1,0 +1,58 @@
+// Shared pieces of the chain-ensemble kernels (chains.cu: SIMT kernels; elm_tc.cu: HMC with the
+// ELM gradient on tensor cores).
+#pragma once
+#include "density.cuh"
+#include "elm.cuh"
+
+namespace hepmc {
+
+struct ChainArgs {
+    const double* x0;
+    int64_t n_chains, first_chain, T, thin, n_kept;
+    uint64_t seed;
+    uint32_t stream_id;
+    const double* z_replay;  // rwm: normals (C, T-1, nd); hmc: momenta (C, T-1, nd)
+    const double* u_replay;  // (C, T-1)
+    double* chain;           // (C, n_kept, nd) or NULL
+    double* last;            // (C, nd)
+    int64_t* accepted;       // (C,)
+    unsigned long long* total_accepted;
+    double scale[HEPMC_MAX_CHAIN_DIM];  // rwm: sqrt(diag cov); hmc: sqrt(mass)
+    int prop_kind;                      // rwm: 0 = Gaussian random walk, 1 = uniform independence on (lo, hi)
+    double prop_lo, prop_hi;
+    // hmc
+    double step_size;
+    int steps;
+    int precision;
+};
+
+// two standard normals from one Philox call (Box-Muller on two 52-bit uniforms)
+__device__ __forceinline__ void normal_pair(const U4& r, double& z0, double& z1) {
+    const double u1 = u52(r.x, r.y), u2 = u52(r.z, r.w);
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    z0 = rad * cs;
+    z1 = rad * sn;
+}
+
+template <int NDIM>
+__device__ __forceinline__ void store_state(double* chain, int64_t c, int64_t n_kept, int64_t slot,
+                                            const double (&x)[NDIM]) {
+    double* o = chain + ((size_t)c * n_kept + slot) * NDIM;
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) o[d] = x[d];
+}
+
+__device__ __forceinline__ void finish_counts(const ChainArgs& a, bool active, int64_t c, int64_t acc) {
+    if (active && a.accepted) a.accepted[c] = acc;
+    const int64_t tot = warp_sum_i64(active ? acc : 0);
+    if ((threadIdx.x & 31) == 0 && a.total_accepted && tot) atomicAdd(a.total_accepted, (unsigned long long)tot);
+}
+
+
+// tensor-core launchers (elm_tc.cu)
+int launch_hmc_tc(const Dens& dens, const Dens& pdist, const hepmc_elm_t& elm, const ChainArgs& a, cudaStream_t st);
+int launch_elm_grad_tc(const hepmc_elm_t& elm, int ndim, const double* xs, int64_t n, double* out, cudaStream_t st);
+
+}  // namespace hepmc

@@ -44,11 +44,7 @@ __device__ __forceinline__ void elm_gradient(int mode, int nodes, const T* __res
 #pragma unroll
     for (int k = 0; k < NDIM; ++k) { xt[k] = (T)x[k]; acc[k] = (T)0; }
     if (mode == HEPMC_GRAD_ELM_GAUSS) {
-        // float64: two nodes in flight and split square sums (the FP64 pipe is latency bound at
-        // the occupancy 168 registers allow); float32: plain loop (issue bound, measured faster)
-        constexpr int UNR = sizeof(T) == 8 ? 2 : 1;
-#pragma unroll UNR
-        for (int i = 0; i < nodes; ++i) {
+        auto node = [&](int i) {
             const T* r = tab + i * row;
             T diff[NDIM];
             T ss0 = (T)0, ss1 = (T)0;
@@ -62,6 +58,14 @@ __device__ __forceinline__ void elm_gradient(int mode, int nodes, const T* __res
             const T gi = -elm_exp(-(ss * r[NDIM])) * r[NDIM + 1];  // basis_function_gradient * ow/w^2
 #pragma unroll
             for (int k = 0; k < NDIM; ++k) acc[k] = fma(gi, diff[k], acc[k]);
+        };
+        if constexpr (sizeof(T) == 8) {
+            // float64: two nodes in flight and split square sums (the FP64 pipe is latency bound
+            // at the occupancy 168 registers allow)
+#pragma unroll 2
+            for (int i = 0; i < nodes; ++i) node(i);
+        } else {
+            for (int i = 0; i < nodes; ++i) node(i);  // float32: compiler's own unrolling (issue bound)
         }
     } else {
         for (int i = 0; i < nodes; ++i) {
