@@ -3,7 +3,8 @@
 //   hmc_tc_kernel      : HMC ensembles (hepmc_hmc_chains, precision = 2): momentum draw,
 //                        leapfrog and the float64 Metropolis test stay per-thread exactly as in
 //                        chains.cu; every gradient evaluation is a CTA-collective GEMM pipeline.
-// Block = 128 compute threads (one chain = one TMEM lane each) + one MMA-issuing warp;
+// Block = 128 owner threads (one chain = one TMEM lane each) + 128 helper threads (exp of the
+// upper half of the S columns) + one MMA-issuing warp;
 // persistent over tiles of 128 chains; node tables are built once per CTA.
 #include "chains.cuh"
 #include "elm_tc.cuh"
@@ -25,13 +26,13 @@ __device__ __forceinline__ TcSetup tc_prologue(unsigned char* smem, const hepmc_
     u.s = carve_tc(smem, u.n_node_tiles);
     u.bars = smem_u32(u.s.bars);
     const int warp = threadIdx.x >> 5;
-    if (warp == TILE_M / 32) tmem_alloc(smem_u32(u.s.tmem_ptr), TMEM_COLS);
+    if (warp == MMA_WARP) tmem_alloc(smem_u32(u.s.tmem_ptr), TMEM_COLS);
     if (threadIdx.x == 0) {
-        mbar_init(u.bars + 8 * BAR_A, N_COMPUTE);
+        mbar_init(u.bars + 8 * BAR_A, N_OWNER / 32);
         mbar_init(u.bars + 8 * BAR_S0, 1);
         mbar_init(u.bars + 8 * BAR_S1, 1);
-        mbar_init(u.bars + 8 * BAR_P0, N_COMPUTE);
-        mbar_init(u.bars + 8 * BAR_P1, N_COMPUTE);
+        mbar_init(u.bars + 8 * BAR_P0, N_COMPUTE / 32);
+        mbar_init(u.bars + 8 * BAR_P1, N_COMPUTE / 32);
         mbar_init(u.bars + 8 * BAR_D2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -49,7 +50,7 @@ __device__ __forceinline__ TcSetup tc_prologue(unsigned char* smem, const hepmc_
 __device__ __forceinline__ void tc_epilogue(const TcSetup& u) {
     fence_before();
     __syncthreads();
-    if ((threadIdx.x >> 5) == TILE_M / 32) tmem_dealloc(u.tmem_base, TMEM_COLS);
+    if ((threadIdx.x >> 5) == MMA_WARP) tmem_dealloc(u.tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ stand-alone gradient
@@ -75,7 +76,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) elm_grad_tc_kernel(const __grid_
                 for (int k = 0; k < D; ++k) out[j * D + k] = g[k];
             }
         }
-    } else if (threadIdx.x == TILE_M) {
+    } else if (warp < MMA_WARP) {
+        ComputeState st;
+        const uint32_t lane_base = u.tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+            exp_half_tiles(st, u.bars, lane_base, elm.nodes, u.n_node_tiles, 1);
+    } else if (threadIdx.x == N_COMPUTE) {
         IssuerState st;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
             issuer_eval(st, u.bars, u.tmem_base, u.b1_saddr, u.b2_saddr, elm.nodes, u.n_node_tiles);
@@ -172,7 +178,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) hmc_tc_kernel(const __grid_const
             }
             finish_counts(a, active, c, acc);
         }
-    } else if (threadIdx.x == TILE_M) {
+    } else if (warp < MMA_WARP) {
+        ComputeState hs;
+        const uint32_t lane_base = u.tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+            for (int64_t e = 0; e < evals_per_tile; ++e)
+                exp_half_tiles(hs, u.bars, lane_base, elm.nodes, u.n_node_tiles, 1);
+    } else if (threadIdx.x == N_COMPUTE) {
         IssuerState st;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
             for (int64_t e = 0; e < evals_per_tile; ++e)
@@ -199,6 +211,10 @@ static int tc_common_checks(const hepmc_elm_t& elm, int ndim, size_t& smem) {
         case 5: MACRO(5); break; case 6: MACRO(6); break; case 7: MACRO(7); break; case 8: MACRO(8); break; \
         default: break;                                                                         \
     }
+
+extern "C" int hepmc_tc_debug(int mode) {
+    return (int)cudaMemcpyToSymbol(tc::g_tc_debug, &mode, sizeof(int));
+}
 
 int launch_elm_grad_tc(const hepmc_elm_t& elm, int ndim, const double* xs, int64_t n, double* out, cudaStream_t st) {
     size_t smem = 0;

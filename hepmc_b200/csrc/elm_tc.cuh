@@ -8,15 +8,17 @@
 //           so S_ji = log2e * (-h_i |x_j - c_i|^2) directly.  Operands are TF32; to keep FP32-level
 //           accuracy through the cancellation both sides are split hi/lo and concatenated along K
 //           ("3xTF32": hi*hi + hi*lo + lo*hi), K1 = 3 (D+2) <= 32 for D <= 8.
-//   P = exp2(S)  (MUFU ex2, rounded to TF32), written back IN PLACE into the S columns of TMEM
+//   P = exp2(S)  (one MUFU.EX2 per pair; the MMA truncates FP32 -> TF32, a uniform -2^-12 relative
+//           scale of the whole gradient; an explicit cvt.rna would double the XU-pipe load),
+//           written back IN PLACE into the S columns of TMEM
 //   GEMM-2  D2 += P . B2^T    B2 row n = coef * c'_n (n < D), coef (n = D)      -> D2 (128 x 16)
 //           grad_jk = D2_jk - x'_jk * D2_jD
 // Both GEMMs take A from TMEM (tcgen05.mma [d], [a], b_desc) and B from shared memory in the
 // canonical K-major no-swizzle layout; node tables for all tiles stay resident in smem
 // (B1: 16 KB, B2: 8 KB per 128 nodes).  One CTA = 128 chains (TMEM lanes) = 4 compute warps +
-// 1 MMA-issuing warp; S is double buffered in TMEM so GEMM-1 of node tile t+1 / GEMM-2 of tile t
+// 4 helper warps (upper half of the S columns) + 1 MMA-issuing warp; S is double buffered in TMEM so GEMM-1 of node tile t+1 / GEMM-2 of tile t
 // overlap the exponentials of the tiles in between.  mbarrier pipeline:
-//   A_ready (128 arrivals) -> [G1(0), G1(1)] -> S_full[b] (commit) -> exp -> P_ready[b] (128)
+//   A_ready (128 arrivals) -> [G1(0), G1(1)] -> S_full[b] (commit) -> exp -> P_ready[b] (256)
 //   -> G2(t), G1(t+2) ... -> D2_full (commit) -> epilogue.
 #pragma once
 #include "common.cuh"
@@ -29,11 +31,14 @@ constexpr int TILE_N = 128;      // nodes per tile
 constexpr int K1 = 32;           // 3 * (D + 2) padded to a multiple of 8, D <= 8
 constexpr int N2 = 16;           // D + 1 padded to the MMA N granularity at M = 128
 constexpr int MAX_D = 8;
-constexpr int COL_A1 = 0, COL_D2 = 32, COL_S0 = 64, COL_S1 = 192, TMEM_COLS = 512;
+constexpr int N_ACC = 1;          // GEMM-2 accumulators (measured: splitting over 4 independent accumulators gains nothing)
+constexpr int COL_A1 = 0, COL_D2 = 32, COL_S0 = 96, COL_S1 = 224, TMEM_COLS = 512;
 constexpr int B1_TILE_BYTES = (K1 / 4) * TILE_N * 16;   // [K chunk][node row][16 B]
 constexpr int B2_TILE_BYTES = (TILE_N / 4) * N2 * 16;   // [node chunk][n row][16 B]
-constexpr int N_COMPUTE = TILE_M;                       // compute threads
-constexpr int N_THREADS = TILE_M + 32;                  // + MMA / allocator warp
+constexpr int N_OWNER = TILE_M;                         // owner threads: one chain = one TMEM lane each
+constexpr int N_COMPUTE = 2 * TILE_M;                   // + helper warps: same lanes, upper half of the S columns
+constexpr int N_THREADS = N_COMPUTE + 32;               // + MMA / allocator warp
+constexpr int MMA_WARP = N_COMPUTE / 32;
 
 __host__ __device__ inline size_t smem_bytes(int nodes) {
     const int nt = (nodes + TILE_N - 1) / TILE_N;
@@ -110,6 +115,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         HEPMC_W8(v, 0), HEPMC_W8(v, 8), HEPMC_W8(v, 16), HEPMC_W8(v, 24)
         : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        HEPMC_W8(v, 0), HEPMC_W8(v, 8)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -138,6 +149,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+
+// development knob (scripts only): 1 = skip GEMM-2, 2 = skip exp, 4 = GEMM-2 with 1 MMA per tile
+__device__ int g_tc_debug = 0;
 
 struct Shared {
     float* b1;           // [n_tiles][K1/4][TILE_N][4]
@@ -220,8 +234,10 @@ struct IssuerState {
 __device__ __forceinline__ void issue_g1(uint32_t tmem_base, uint32_t b1_saddr, int t, int n_cols) {
     const uint32_t d = tmem_base + ((t & 1) ? COL_S1 : COL_S0);
     const uint32_t idesc = make_idesc(TILE_M, n_cols);
+    const int nks = (g_tc_debug & 8) ? 1 : K1 / 8;
 #pragma unroll
     for (int ks = 0; ks < K1 / 8; ++ks) {
+        if (ks >= nks) break;
         const uint64_t bd = make_desc(b1_saddr + t * B1_TILE_BYTES + ks * 2 * (TILE_N * 16), TILE_N * 16, 128);
         umma_tf32_ts(d, tmem_base + COL_A1 + ks * 8, bd, idesc, ks > 0 ? 1u : 0u);
     }
@@ -231,7 +247,7 @@ __device__ __forceinline__ void issue_g2(uint32_t tmem_base, uint32_t b2_saddr, 
     const uint32_t idesc = make_idesc(TILE_M, N2);
     for (int ks = 0; ks < n_cols / 8; ++ks) {
         const uint64_t bd = make_desc(b2_saddr + t * B2_TILE_BYTES + ks * 2 * (N2 * 16), N2 * 16, 128);
-        umma_tf32_ts(tmem_base + COL_D2, a + ks * 8, bd, idesc, (first && ks == 0) ? 0u : 1u);
+        umma_tf32_ts(tmem_base + COL_D2 + (ks % N_ACC) * N2, a + ks * 8, bd, idesc, (first && ks < N_ACC) ? 0u : 1u);
     }
 }
 
@@ -256,7 +272,7 @@ __device__ __forceinline__ void issuer_eval(IssuerState& st, uint32_t bars, uint
         if (t & 1) { mbar_wait(bars + 8 * BAR_P1, st.ph_p1); st.ph_p1 ^= 1; }
         else { mbar_wait(bars + 8 * BAR_P0, st.ph_p0); st.ph_p0 ^= 1; }
         fence_after();
-        issue_g2(tmem_base, b2_saddr, t, tile_cols(nodes, t), t == 0);
+        if (!(g_tc_debug & 1)) issue_g2(tmem_base, b2_saddr, t, (g_tc_debug & 4) ? 8 : tile_cols(nodes, t), t == 0);
         if (t + 2 < n_tiles) {
             issue_g1(tmem_base, b1_saddr, t + 2, tile_cols(nodes, t + 2));
             umma_commit(bars + 8 * ((t & 1) ? BAR_S1 : BAR_S0));
@@ -269,6 +285,48 @@ __device__ __forceinline__ void issuer_eval(IssuerState& st, uint32_t bars, uint
 struct ComputeState {
     uint32_t ph_s0 = 0, ph_s1 = 0, ph_d2 = 0;
 };
+
+// S -> P = exp2(S) in place for one half (64 columns) of every node tile of one gradient
+// evaluation.  half 0: owner warps, half 1: helper warps (same TMEM lanes, warp % 4 equal).
+__device__ __forceinline__ void exp_half_tiles(ComputeState& st, uint32_t bars, uint32_t tmem_lane_base, int nodes,
+                                               int n_tiles, int half) {
+    for (int t = 0; t < n_tiles; ++t) {
+        const uint32_t col = ((t & 1) ? COL_S1 : COL_S0) + half * 64;
+        if (t & 1) { mbar_wait(bars + 8 * BAR_S1, st.ph_s1); st.ph_s1 ^= 1; }
+        else { mbar_wait(bars + 8 * BAR_S0, st.ph_s0); st.ph_s0 ^= 1; }
+        fence_after();
+        const int my_cols = tile_cols(nodes, t) - half * 64;   // columns of this half that GEMM-2 reads
+        if (my_cols > 0 && !(g_tc_debug & 2)) {
+            // software pipeline over 16-column chunks: the TMEM read of chunk c+1 is in flight
+            // while the MUFU works on chunk c (TMEM read and MUFU both run at 4 values/clk/SMSP)
+            const int nch = my_cols >= 64 ? 4 : (my_cols >> 4);
+            uint32_t va[16], vb[16];
+            tmem_ld16(tmem_lane_base + col, va);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c < nch) {
+                    if (c & 1) {
+                        if (c + 1 < nch) tmem_ld16(tmem_lane_base + col + (c + 1) * 16, va);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) vb[j] = __float_as_uint(ex2_approx(__uint_as_float(vb[j])));
+                        tmem_st16(tmem_lane_base + col + c * 16, vb);
+                    } else {
+                        if (c + 1 < nch) tmem_ld16(tmem_lane_base + col + (c + 1) * 16, vb);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) va[j] = __float_as_uint(ex2_approx(__uint_as_float(va[j])));
+                        tmem_st16(tmem_lane_base + col + c * 16, va);
+                    }
+                    if (c + 1 < nch) tmem_wait_ld();
+                }
+            }
+            tmem_wait_st();
+        }
+        fence_before();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(bars + 8 * ((t & 1) ? BAR_P1 : BAR_P0));  // one arrival per warp
+    }
+}
 
 template <int D>
 __device__ __forceinline__ void compute_eval(ComputeState& st, uint32_t bars, uint32_t tmem_lane_base, int nodes,
@@ -312,34 +370,26 @@ __device__ __forceinline__ void compute_eval(ComputeState& st, uint32_t bars, ui
     tmem_st32(tmem_lane_base + COL_A1, a1);
     tmem_wait_st();
     fence_before();
-    mbar_arrive(bars + 8 * BAR_A);
-    for (int t = 0; t < n_tiles; ++t) {
-        const uint32_t col = (t & 1) ? COL_S1 : COL_S0;
-        if (t & 1) { mbar_wait(bars + 8 * BAR_S1, st.ph_s1); st.ph_s1 ^= 1; }
-        else { mbar_wait(bars + 8 * BAR_S0, st.ph_s0); st.ph_s0 ^= 1; }
-        fence_after();
-        const int nblk = (tile_cols(nodes, t) + 31) >> 5;
-        for (int cb = 0; cb < nblk; ++cb) {
-            uint32_t v[32];
-            tmem_ld32(tmem_lane_base + col + cb * 32, v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = to_tf32_rna(ex2_approx(__uint_as_float(v[j])));
-            tmem_st32(tmem_lane_base + col + cb * 32, v);
-        }
-        tmem_wait_st();
-        fence_before();
-        mbar_arrive(bars + 8 * ((t & 1) ? BAR_P1 : BAR_P0));
-    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bars + 8 * BAR_A);  // one arrival per warp
+    exp_half_tiles(st, bars, tmem_lane_base, nodes, n_tiles, 0);
     mbar_wait(bars + 8 * BAR_D2, st.ph_d2);
     st.ph_d2 ^= 1;
     fence_after();
-    uint32_t d2[16];
-    tmem_ld16(tmem_lane_base + COL_D2, d2);
-    tmem_wait_ld();
-    const float sum = __uint_as_float(d2[D]);
+    float acc[D + 1];
 #pragma unroll
-    for (int k = 0; k < D; ++k) g[k] = (double)(__uint_as_float(d2[k]) - xc[k] * sum);
+    for (int k = 0; k <= D; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int q = 0; q < N_ACC; ++q) {
+        uint32_t d2[16];
+        tmem_ld16(tmem_lane_base + COL_D2 + q * N2, d2);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k <= D; ++k) acc[k] += __uint_as_float(d2[k]);
+    }
+    const float sum = acc[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) g[k] = (double)(acc[k] - xc[k] * sum);
 }
 
 }  // namespace tc
