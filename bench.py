@@ -214,7 +214,7 @@ def run_b200(args):
 
     others = {}
     if rank == 0 and not args.no_others:
-        others = other_workloads(H, _lib, torch, fp64_peak)
+        others = other_workloads(H, _lib, torch, fp64_peak, world == 1 and not args.no_cpu)
 
     if rank != 0:
         if world > 1:
@@ -259,8 +259,54 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def other_workloads(H, _lib, torch, fp64_peak):
-    """The other two metrics BASELINE.json names, single GPU, device-timed."""
+def _best_of(fn, reps=3):
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def cpu_ports():
+    """Single-core NumPy-port timings of the other configs at CPU-feasible sizes."""
+    from oracle import hepmc_oracle as O
+    rs = np.random.RandomState(1234)
+    out = {}
+    n = 1_000_000
+    t = _best_of(lambda: O.plain_mc(O.camel_pdf, rs.random_sample((n, 2))))
+    out["plain2"] = {"value": n / t, "unit": "points/s", "cores": 1, "kind": "port", "sample": "PlainMC(2)(Camel(2), 1e6)"}
+
+    def vegas2():
+        idx = rs.randint(0, 50, (10, 2, 100_000))
+        u = rs.rand(10, 2, 100_000)
+        O.vegas(O.camel_pdf, 2, 50, idx, u)
+    t = _best_of(vegas2, 2)
+    out["vegas2"] = {"value": 1e6 / t, "unit": "points/s", "cores": 1, "kind": "port",
+                     "sample": "VegasMC(2, divisions=50)(Camel(2), 1e5, 10)"}
+    xs = rs.random_sample((n, 16))
+    t = _best_of(lambda: O.rambo_map(xs, 100., 4))
+    out["rambo"] = {"value": n / t, "unit": "PS-points/s", "cores": 1, "kind": "port", "sample": "Rambo(100, 4).map on 1e6 x 16"}
+    C, T = 2000, 51
+    z, u = rs.standard_normal((C, T - 1, 2)), rs.rand(C, T - 1)
+    t = _best_of(lambda: O.metropolis_chains(O.banana_pdf, np.tile([0., 10.], (C, 1)), z, u, np.sqrt([10., 10.])), 2)
+    out["rwm"] = {"value": C * (T - 1) / t, "unit": "chain-steps/s", "cores": 1, "kind": "port",
+                  "sample": "banana-2D RWM, NumPy port vectorised over 2000 chains x 50 steps (the reference itself "
+                            "steps ONE chain in a Python loop: 6.2e3 steps/s, BASELINE.md)"}
+    for nodes in (100, 1024):
+        centers, widths, w = rs.random_sample((nodes, 8)), 0.01 + 0.99 * rs.random_sample(nodes), 0.01 * rs.standard_normal(nodes)
+        C, T = 200, 3
+        p, uu = rs.standard_normal((C, T - 1, 8)), rs.rand(C, T - 1)
+        grad = lambda q: O.elm_gauss_eval_gradient(q, centers, widths, w)
+        t = _best_of(lambda: O.hmc_chains(O.camel_pdf, grad, np.full((C, 8), 1 / 3), p, uu, 1.0, 0.01, 20), 1)
+        out["hmc_elm%d" % nodes] = {"value": C * (T - 1) / t, "unit": "chain-steps/s", "cores": 1, "kind": "port",
+                                    "sample": "camel-8D HMC + GaussianBasis(%d) gradient, NumPy port vectorised over 200 chains x 2 "
+                                              "steps x 20 leapfrog (reference, one chain: 770 / 311 steps/s, BASELINE.md)" % nodes}
+    return out
+
+
+def other_workloads(H, _lib, torch, fp64_peak, with_cpu):
+    """The other configs BASELINE.json names, single GPU, device-timed."""
     out = {}
 
     def timed(fn, reps=3):
@@ -280,7 +326,17 @@ def other_workloads(H, _lib, torch, fp64_peak):
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         hbm = 6650.0
-    # RAMBO 2->4, sqrt(s) = 100 GeV: 2^27 points per launch (16 GiB of output, larger than L2)
+    cpu = cpu_ports() if with_cpu else {}
+    # C1: 2-D camel, 1M points: plain MC and VEGAS 10 x 1e5 (launch-latency dominated at this size)
+    camel2 = H.densities.Camel(2)
+    t = timed(lambda: H.PlainMC(2)(camel2, 1_000_000, keep_samples=False))
+    out["c1_plain2"] = {"metric": "camel-2D plain MC points/s (1e6 points, whole call)", "value": 1e6 / t,
+                        "cpu_baseline": cpu.get("plain2")}
+    mc2 = H.VegasMC(2, divisions=50)
+    t = timed(lambda: mc2(camel2, 100_000, 10, keep_samples=False))
+    out["c1_vegas2"] = {"metric": "camel-2D VEGAS points/s (10 x 1e5 points, whole call)", "value": 1e6 / t,
+                        "cpu_baseline": cpu.get("vegas2")}
+    # C2: RAMBO 2->4, sqrt(s) = 100 GeV: 2^27 points per launch (16 GiB of output, larger than L2)
     m = H.phase_space.Rambo(100., 4)
     nr = 1 << 27
     buf = torch.empty((nr, 16), dtype=torch.float64, device="cuda")
@@ -288,16 +344,19 @@ def other_workloads(H, _lib, torch, fp64_peak):
     del buf
     out["rambo"] = {"metric": "RAMBO 2->4 PS-points/s", "value": nr / t, "points": nr,
                     "roofline": {"bound": "hbm", "achieved": nr * 128 / t / 1e9, "peak": hbm, "unit": "GB/s",
-                                 "frac": nr * 128 / t / 1e9 / hbm, "bytes_per_point": 128}}
-    # banana 2-D RWM: 1e6 chains x 1e3 steps per launch (the 1e4-step config is 10 such launches)
+                                 "frac": nr * 128 / t / 1e9 / hbm, "bytes_per_point": 128,
+                                 "fp64_tflops_algorithmic": 183 * nr / t / 1e12},
+                    "cpu_baseline": cpu.get("rambo")}
+    # C4: banana 2-D RWM: 1e6 chains x 1e3 steps per launch (the 1e4-step config is 10 such launches)
     C, T = 1_000_000, 1001
     met = H.DefaultMetropolis(2, H.densities.Banana(2), H.proposals.Gaussian(2, cov=10 * np.eye(2)))
     x0 = torch.tensor([[0., 10.]], device="cuda", dtype=torch.float64).repeat(C, 1)
     t = timed(lambda: met.sample(T, x0, store_chain=False))
     out["rwm"] = {"metric": "banana-2D RWM chain-steps/s", "value": C * (T - 1) / t, "chains": C, "steps": T - 1,
                   "roofline": {"bound": "fp64_simt", "achieved": 23 * C * (T - 1) / t / 1e12, "peak": fp64_peak,
-                               "unit": "TFLOP/s", "frac": 23 * C * (T - 1) / t / 1e12 / fp64_peak, "flop_per_step": 23}}
-    # camel-8D HMC, ELM Gaussian-basis surrogate gradient, 1e5 chains x 20 leapfrog
+                               "unit": "TFLOP/s", "frac": 23 * C * (T - 1) / t / 1e12 / fp64_peak, "flop_per_step": 23},
+                  "cpu_baseline": cpu.get("rwm")}
+    # C5: camel-8D HMC, ELM Gaussian-basis surrogate gradient, 1e5 chains x 20 leapfrog
     rs = np.random.default_rng(0)
     for nodes in (100, 1024):
         basis = H.surrogate.GaussianBasis(8)
@@ -313,7 +372,8 @@ def other_workloads(H, _lib, torch, fp64_peak):
             flop = 21 * (4 * nodes * 8 + 5 * nodes + 4 * 8) + 20 * 64 + 72 + 48
             out["hmc_elm%d_%s" % (nodes, prec)] = {
                 "metric": "camel-8D HMC+ELM chain-steps/s", "value": Ch * (Th - 1) / t, "nodes": nodes,
-                "achieved_tflops": flop * Ch * (Th - 1) / t / 1e12}
+                "achieved_tflops": flop * Ch * (Th - 1) / t / 1e12,
+                "cpu_baseline": cpu.get("hmc_elm%d" % nodes)}
     return out
 
 

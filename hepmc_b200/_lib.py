@@ -19,7 +19,7 @@ PDF, POT, POT_GRADIENT, PDF_GRADIENT = range(4)
 GRAD_EXACT, GRAD_ELM_GAUSS, GRAD_ELM_TRIG = range(3)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhepmc_b200.so")
+LIB_PATH = os.environ.get("HEPMC_B200_LIB", os.path.join(_HERE, "libhepmc_b200.so"))  # override: development A/B builds
 
 
 class DensityBlock(ctypes.Structure):

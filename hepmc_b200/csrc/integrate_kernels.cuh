@@ -7,6 +7,15 @@
 namespace hepmc {
 
 constexpr int kBinWords = HEPMC_MAX_DIM / 4 + 1;  // packed bin bytes per point, padded (bank-conflict-free)
+constexpr int kMaxPPI = 2;        // warp tiles staged per loop trip (shared-memory sizing)
+#ifndef HEPMC_FAST_PPI
+#define HEPMC_FAST_PPI 1
+#endif
+#ifndef HEPMC_FAST_MINBLOCKS
+#define HEPMC_FAST_MINBLOCKS 3
+#endif
+constexpr int kFastPPI = HEPMC_FAST_PPI;
+constexpr int kFastMinBlocks = HEPMC_FAST_MINBLOCKS;
 
 struct SampleArgs {
     const double* grid;  // VEGAS: (ndim, 2K+1); plain: unused
@@ -44,22 +53,43 @@ __device__ __forceinline__ void warp_hist_update(double* hist_w, const double* w
     }
 }
 
+#ifndef HEPMC_HIST_PAIR
+#define HEPMC_HIST_PAIR 0
+#endif
 template <int NDIM>
 __device__ __forceinline__ void warp_hist_update_n(double* hist_w, const double* wf_w, const uint32_t* bins_w,
                                                    int lane) {
     constexpr int ngrp = 32 / NDIM;
+    constexpr int NUPD = (32 + ngrp - 1) / ngrp;  // updates per lane (points grp, grp+ngrp, ...)
     if (lane < ngrp * NDIM) {
         const int d = lane % NDIM, grp = lane / NDIM;
         const int word = d >> 2, shift = 8 * (d & 3);
         const uint32_t* bw = bins_w + grp * kBinWords + word;
         const double* wv = wf_w + grp;
         double* hcol = hist_w + lane;
+        if constexpr (HEPMC_HIST_PAIR && (32 % ngrp == 0) && (NUPD % 2 == 0)) {
+            // two read-modify-writes in flight: both column entries are loaded before the first
+            // add; if the two bins coincide the second add takes the first result (same order of
+            // additions as the sequential loop, so results are bit-identical)
 #pragma unroll
-        for (int i = 0; i < (32 + ngrp - 1) / ngrp; ++i) {
-            if (grp + i * ngrp < 32) {
-                const double v = wv[i * ngrp];
-                const uint32_t bin = (bw[i * ngrp * kBinWords] >> shift) & 0xffu;
-                hcol[bin * 32] += v;
+            for (int i = 0; i < NUPD; i += 2) {
+                const double v0 = wv[i * ngrp], v1 = wv[(i + 1) * ngrp];
+                const uint32_t b0 = (bw[i * ngrp * kBinWords] >> shift) & 0xffu;
+                const uint32_t b1 = (bw[(i + 1) * ngrp * kBinWords] >> shift) & 0xffu;
+                const double h0 = hcol[b0 * 32], h1 = hcol[b1 * 32];
+                const double t0 = h0 + v0;
+                const double t1 = (b1 == b0 ? t0 : h1) + v1;
+                hcol[b0 * 32] = t0;
+                hcol[b1 * 32] = t1;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NUPD; ++i) {
+                if (grp + i * ngrp < 32) {
+                    const double v = wv[i * ngrp];
+                    const uint32_t bin = (bw[i * ngrp * kBinWords] >> shift) & 0xffu;
+                    hcol[bin * 32] += v;
+                }
             }
         }
     }
@@ -90,8 +120,8 @@ __host__ __device__ inline size_t vegas_smem_bytes(int ndim, int K, int threads)
     size_t b = (size_t)ndim * (2 * K + 1) * 8;  // grid
     b += 32 * sizeof(Stats);                    // block merge scratch
     b += (size_t)nw * K * 32 * 8;               // private histogram columns
-    b += (size_t)nw * 32 * 8;                   // wf tile
-    b += (size_t)nw * 32 * kBinWords * 4;       // packed bins tile
+    b += (size_t)nw * 32 * 8 * kMaxPPI;                   // wf tiles
+    b += (size_t)nw * 32 * kBinWords * 4 * kMaxPPI;       // packed bins tiles
     return b;
 }
 
@@ -101,7 +131,7 @@ __device__ __forceinline__ SmemLayout carve(double* base, int ndim, int K, int n
     s.stats = reinterpret_cast<Stats*>(s.grid + (size_t)ndim * (2 * K + 1));
     s.hist = reinterpret_cast<double*>(s.stats + 32);
     s.wf = s.hist + (size_t)nw * K * 32;
-    s.bins = reinterpret_cast<uint32_t*>(s.wf + nw * 32);
+    s.bins = reinterpret_cast<uint32_t*>(s.wf + nw * 32 * kMaxPPI);
     return s;
 }
 
@@ -112,7 +142,7 @@ __device__ __forceinline__ SmemLayout carve(double* base, int ndim, int K, int n
 //       x / f / w / idx outputs are honoured through warp-uniform runtime flags.
 // Shared grid layout: per axis K entries of (bound_k, size_k) as double2 -> one LDS.128.
 template <int KIND, int NDIM_T, bool FAST>
-__global__ void __launch_bounds__(256, FAST ? 3 : 1) vegas_sample_kernel(const __grid_constant__ Dens dens,
+__global__ void __launch_bounds__(256, FAST ? kFastMinBlocks : 1) vegas_sample_kernel(const __grid_constant__ Dens dens,
                                                            const __grid_constant__ SampleArgs a) {
     extern __shared__ double smem_raw[];
     const int ndim = NDIM_T ? NDIM_T : a.ndim;
@@ -120,6 +150,9 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 1) vegas_sample_kernel(const _
     const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SmemLayout s = carve(smem_raw, ndim, K, nw);
     constexpr bool fused = KIND != HEPMC_NONE;
+    // points per thread and loop trip: two independent points in flight on the throughput path
+    // (more ILP against the dependent Philox / FP64 chains); identical results either way
+    constexpr int PPI = FAST ? kFastPPI : 1;
     double2* s_grid2 = reinterpret_cast<double2*>(s.grid);  // [ndim][K] (bound, size); 2K <= 2K+1 doubles per axis
 
     for (int i = threadIdx.x; i < ndim * K; i += blockDim.x) {
@@ -132,8 +165,8 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 1) vegas_sample_kernel(const _
     __syncthreads();
 
     double* hist_w = s.hist + (size_t)warp * K * 32;
-    double* wf_w = s.wf + warp * 32;
-    uint32_t* bins_w = s.bins + warp * 32 * kBinWords;
+    double* wf_w = s.wf + warp * 32 * kMaxPPI;
+    uint32_t* bins_w = s.bins + warp * 32 * kBinWords * kMaxPPI;
 
     const PhiloxKey key = philox_expand(a.seed);
     const bool replay = !FAST && a.u_replay != nullptr;
@@ -144,73 +177,92 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 1) vegas_sample_kernel(const _
     ShiftedAcc acc;
     acc.init();
 
-    for (int it = 0; it < ppt; ++it) {
-        const int64_t li = chunk0 + (int64_t)it * blockDim.x + threadIdx.x;
-        const bool valid = li < a.n;
-        double wf = 0.0;
-        uint32_t packed[NPACK];
+    // one sample point: draws -> grid map -> integrand -> weight; returns f*w and the packed bins
+    auto point = [&](int64_t li, double& wf, uint32_t (&packed)[NPACK]) {
+        const uint64_t g = (uint64_t)(a.first_index + li);
+        PdfAcc pa;
+        pa.init();
+        double w = 1.0;
 #pragma unroll
-        for (int q = 0; q < NPACK; ++q) packed[q] = 0u;
-        if (valid) {
-            const uint64_t g = (uint64_t)(a.first_index + li);
-            PdfAcc pa;
-            pa.init();
-            double w = 1.0;
+        for (int call = 0; call < ncalls; ++call) {
+            U4 r{0u, 0u, 0u, 0u};
+            if (FAST || !replay) r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)call, a.stream_id, key);
 #pragma unroll
-            for (int call = 0; call < ncalls; ++call) {
-                U4 r{0u, 0u, 0u, 0u};
-                if (FAST || !replay) r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)call, a.stream_id, key);
+            for (int h = 0; h < 2; ++h) {
+                const int d = 2 * call + h;
+                if (d < ndim) {
+                    uint32_t bin;
+                    double frac;
+                    if (!FAST && replay) {
+                        bin = (uint32_t)a.idx_replay[(int64_t)d * a.n + li];
+                        frac = a.u_replay[(int64_t)d * a.n + li];
+                    } else {
+                        bin_frac(h ? r.z : r.x, h ? r.w : r.y, (uint32_t)K, bin, frac);
+                    }
+                    const double2 bs = s_grid2[d * K + bin];
+                    const double x = fma(bs.y, frac, bs.x);  // stratified_volume.py:119-121
+                    w *= bs.y;                               // vegas.py:69-70
+                    if constexpr (fused) pdf_acc_dim<KIND, 1>(dens, pa, d, x);
+                    if constexpr (NDIM_T != 0) {
+                        packed[d >> 2] |= bin << (8 * (d & 3));
+                    } else {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int d = 2 * call + h;
-                    if (d < ndim) {
-                        uint32_t bin;
-                        double frac;
-                        if (!FAST && replay) {
-                            bin = (uint32_t)a.idx_replay[(int64_t)d * a.n + li];
-                            frac = a.u_replay[(int64_t)d * a.n + li];
-                        } else {
-                            bin_frac(h ? r.z : r.x, h ? r.w : r.y, (uint32_t)K, bin, frac);
-                        }
-                        const double2 bs = s_grid2[d * K + bin];
-                        const double x = fma(bs.y, frac, bs.x);  // stratified_volume.py:119-121
-                        w *= bs.y;                               // vegas.py:69-70
-                        if constexpr (fused) pdf_acc_dim<KIND, 1>(dens, pa, d, x);
-                        if constexpr (NDIM_T != 0) {
-                            packed[d >> 2] |= bin << (8 * (d & 3));
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < NPACK; ++q)
-                                if (q == (d >> 2)) packed[q] |= bin << (8 * (d & 3));
-                        }
-                        if constexpr (!FAST) {
-                            if (a.x_out) a.x_out[(int64_t)d * a.n + li] = x;
-                            if (a.idx_out) a.idx_out[(int64_t)d * a.n + li] = (int64_t)bin;
-                        }
+                        for (int q = 0; q < NPACK; ++q)
+                            if (q == (d >> 2)) packed[q] |= bin << (8 * (d & 3));
+                    }
+                    if constexpr (!FAST) {
+                        if (a.x_out) a.x_out[(int64_t)d * a.n + li] = x;
+                        if (a.idx_out) a.idx_out[(int64_t)d * a.n + li] = (int64_t)bin;
                     }
                 }
             }
-            w *= a.kpow;  // vegas.py:72 (partition_count evaluated in floating point, App. B1)
+        }
+        w *= a.kpow;  // vegas.py:72 (partition_count evaluated in floating point, App. B1)
+        if constexpr (!FAST) {
+            if (a.w_out) a.w_out[li] = w;
+        }
+        if constexpr (fused) {
+            const double f = pdf_acc_finish<KIND>(dens, pa);
+            wf = f * w;  // vegas.py:104
             if constexpr (!FAST) {
-                if (a.w_out) a.w_out[li] = w;
+                if (a.f_out) a.f_out[li] = f;
             }
-            if constexpr (fused) {
-                const double f = pdf_acc_finish<KIND>(dens, pa);
-                wf = f * w;  // vegas.py:104
-                acc.add(wf);
-                if constexpr (!FAST) {
-                    if (a.f_out) a.f_out[li] = f;
-                }
+        }
+    };
+
+    for (int it = 0; it < ppt; it += PPI) {
+        double wf[PPI];
+        uint32_t packed[PPI][NPACK];
+        bool valid[PPI];
+#pragma unroll
+        for (int u = 0; u < PPI; ++u) {
+            const int64_t li = chunk0 + (int64_t)(it + u) * blockDim.x + threadIdx.x;
+            valid[u] = li < a.n;
+            wf[u] = 0.0;
+#pragma unroll
+            for (int q = 0; q < NPACK; ++q) packed[u][q] = 0u;
+            if constexpr (FAST) {
+                point(li, wf[u], packed[u]);  // branch-free: out-of-range points touch no memory and are masked below
+            } else {
+                if (valid[u]) point(li, wf[u], packed[u]);
             }
         }
         if constexpr (fused) {
-            wf_w[lane] = wf;
 #pragma unroll
-            for (int q = 0; q < NPACK; ++q)
-                if (q * 4 < ndim) bins_w[lane * kBinWords + q] = packed[q];
+            for (int u = 0; u < PPI; ++u) {
+                if (valid[u]) acc.add(wf[u]);
+                else wf[u] = 0.0;
+                wf_w[u * 32 + lane] = wf[u];
+#pragma unroll
+                for (int q = 0; q < NPACK; ++q)
+                    if (q * 4 < ndim) bins_w[(u * 32 + lane) * kBinWords + q] = packed[u][q];
+            }
             __syncwarp();
-            if constexpr (NDIM_T != 0) warp_hist_update_n<NDIM_T>(hist_w, wf_w, bins_w, lane);
-            else warp_hist_update(hist_w, wf_w, bins_w, ndim, lane);
+#pragma unroll
+            for (int u = 0; u < PPI; ++u) {
+                if constexpr (NDIM_T != 0) warp_hist_update_n<NDIM_T>(hist_w, wf_w + u * 32, bins_w + u * 32 * kBinWords, lane);
+                else warp_hist_update(hist_w, wf_w + u * 32, bins_w + u * 32 * kBinWords, ndim, lane);
+            }
             __syncwarp();
         }
     }
