@@ -12,6 +12,9 @@ import torch
 
 MAX_DIM = 32
 MAX_CHAIN_DIM = 16
+MAX_CHANNELS = 16
+CHANNEL_DIM = 16
+CHANNEL_ROW = 8 + 3 * CHANNEL_DIM
 N_SLOTS = 8
 
 CAMEL, UCAMEL, BANANA, GAUSSIAN, UNIFORM, NONE = range(6)
@@ -63,6 +66,9 @@ SIGNATURES = {
     "hepmc_vegas_integrate": (_int, [_dens_p, _vp, _int, _int, _i64, _int, _dbl, _u64, _u32,
                                      _vp, _vp, _i64, _vp]),
     "hepmc_grid_pdf": (_int, [_vp, _int, _int, _vp, _i64, _vp, _vp]),
+    "hepmc_multichannel_sample": (_int, [_dens_p, _vp, _int, _int, _i64, _i64, _i64, _u64, _u32,
+                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hepmc_multichannel_accumulate": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _vp, _vp, _vp]),
     "hepmc_rambo_map": (_int, [_int, _dbl, _i64, _i64, _u64, _u32, _vp, _vp, _vp]),
     "hepmc_rambo_pdf": (_dbl, [_int, _dbl]),
     "hepmc_rwm_chains": (_int, [_dens_p, _vp, _int, ctypes.POINTER(_dbl), _i64, _i64, _i64, _i64, _u64, _u32,

@@ -1,6 +1,8 @@
 from .integration import PlainMC, IntegrationSample
-from .importance import ImportanceMC
+from .importance import ImportanceMC, MultiChannelMC
 from .vegas import VegasMC, VegasSample
 from .stratified_volume import GridVolumes
+from .multi_channel import MultiChannel, ChannelsSample
 
-__all__ = ['PlainMC', 'ImportanceMC', 'VegasMC', 'GridVolumes', 'IntegrationSample', 'VegasSample']
+__all__ = ['PlainMC', 'ImportanceMC', 'MultiChannelMC', 'VegasMC', 'GridVolumes', 'MultiChannel',
+           'IntegrationSample', 'VegasSample', 'ChannelsSample']

@@ -10,7 +10,9 @@
 //           ("3xTF32": hi*hi + hi*lo + lo*hi), K1 = 3 (D+2) <= 32 for D <= 8.
 //   P = exp2(S)  (one MUFU.EX2 per pair; the MMA truncates FP32 -> TF32, a uniform -2^-12 relative
 //           scale of the whole gradient; an explicit cvt.rna would double the XU-pipe load),
-//           written back IN PLACE into the S columns of TMEM
+//           written back IN PLACE into the S columns of TMEM.  P and B2 stay TF32 (8-bit exponent):
+//           trained ELM weights reach 1e6..1e10 with heavy cancellation, so tiny P still matter;
+//           an F16 GEMM-2 (half the MMA count) was measured 11% faster but loses those terms.
 //   GEMM-2  D2 += P . B2^T    B2 row n = coef * c'_n (n < D), coef (n = D)      -> D2 (128 x 16)
 //           grad_jk = D2_jk - x'_jk * D2_jD
 // Both GEMMs take A from TMEM (tcgen05.mma [d], [a], b_desc) and B from shared memory in the
@@ -331,37 +333,37 @@ __device__ __forceinline__ void exp_half_tiles(ComputeState& st, uint32_t bars, 
 template <int D>
 __device__ __forceinline__ void compute_eval(ComputeState& st, uint32_t bars, uint32_t tmem_lane_base, int nodes,
                                              int n_tiles, const double (&x)[D], double (&g)[D]) {
-    // A1 row: [hi(a), hi(a), lo(a)] with a = [x', |x'|^2, 1]
+    // A1 row: [hi(a), hi(a), lo(a)] with a = [x', |x'|^2, 1]; single precision is enough for the
+    // split (hi + lo carries 22 bits), the double -> float conversion happens once per coordinate
     uint32_t a1[32];
     float xc[D];
     {
-        double av[D + 2];
-        double r2 = 0.0;
+        float av[D + 2];
+        float r2 = 0.f;
         bool finite = true;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            av[k] = x[k] - 0.5;
-            finite = finite && (fabs(av[k]) < 1.0e6);
-            r2 += av[k] * av[k];
+            av[k] = (float)(x[k] - 0.5);
+            finite = finite && (fabsf(av[k]) < 1.0e6f);
+            r2 = fmaf(av[k], av[k], r2);
         }
         av[D] = r2;
-        av[D + 1] = 1.0;
+        av[D + 1] = 1.f;
         // non-finite / runaway positions (diverged trajectories) are mapped to a far-away finite
         // point: every exponent underflows, the gradient is 0 and the MH test rejects on pdf = 0
         if (!finite) {
 #pragma unroll
-            for (int k = 0; k < D; ++k) av[k] = 0.0;
-            av[D] = 1.0e12;
+            for (int k = 0; k < D; ++k) av[k] = 0.f;
+            av[D] = 1.0e12f;
         }
 #pragma unroll
-        for (int k = 0; k < D; ++k) xc[k] = (float)av[k];
+        for (int k = 0; k < D; ++k) xc[k] = av[k];
 #pragma unroll
         for (int k = 0; k < 32; ++k) a1[k] = 0u;
 #pragma unroll
         for (int k = 0; k < D + 2; ++k) {
-            const double a = av[k];
-            const float hi = tf32_trunc((float)a);
-            const float lo = (float)(a - (double)hi);
+            const float hi = tf32_trunc(av[k]);
+            const float lo = av[k] - hi;
             a1[k] = __float_as_uint(hi);
             a1[(D + 2) + k] = __float_as_uint(hi);
             a1[2 * (D + 2) + k] = __float_as_uint(lo);

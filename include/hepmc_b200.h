@@ -36,6 +36,9 @@ extern "C" {
 #define HEPMC_MAX_DIM 32          /* max dimensionality of a built-in density      */
 #define HEPMC_MAX_DIVISIONS 255   /* max VEGAS bins per axis (bin ids are bytes)    */
 #define HEPMC_N_SLOTS 8           /* fixed reduction slots: GPU-count invariance    */
+#define HEPMC_MAX_CHANNELS 16      /* multi-channel importance sampling                */
+#define HEPMC_MAX_CHANNEL_DIM 16
+#define HEPMC_CHANNEL_ROW (8 + 3 * HEPMC_MAX_CHANNEL_DIM)
 
 /* error codes (negative); positive values are cudaError_t */
 #define HEPMC_E_ARG (-1)          /* bad argument (null pointer, size, kind)        */
@@ -171,6 +174,31 @@ int hepmc_vegas_integrate(const hepmc_density_t* dens, double* grid_dev, int ndi
 /* GridVolumes.pdf (stratified_volume.py:74-83, default base counts): xs (n, ndim) -> (n,) */
 int hepmc_grid_pdf(const double* grid_dev, int ndim, int divisions, const double* xs_dev,
                    int64_t n, double* out_dev, void* stream);
+
+/* ---- multi-channel importance sampling ("next" row 1): replaces MultiChannel.rvs/pdf/sample
+ * (core/integration/multi_channel.py:103-160) and the sampling + reduction half of
+ * MultiChannelMC.iterate (importance.py:141-175) ------------------------------------------ */
+/* channel_table_dev: (n_channels, HEPMC_CHANNEL_ROW) doubles, one row per channel:
+ *   [0] kind (HEPMC_GAUSSIAN | HEPMC_UNIFORM), [1] channel weight alpha,
+ *   GAUSSIAN: [2] n*log(2pi) + sum(log cov_d), [8+d] mean_d, [8+16+d] sqrt(cov_d), [8+32+d] sqrt(1/cov_d)
+ *   UNIFORM : [2] low, [3] high, [4] volume.
+ * Point i (global index first_index + i) picks its channel with probability alpha (i.i.d.
+ * categorical = multinomial counts, multi_channel.py:141), is drawn from it, and the mixture
+ * density p = sum_c alpha_c p_c(x) (:103-114) is evaluated.  Replay: xs_replay_dev (n, ndim)
+ * and ch_replay_dev (n,) int64 (the reference's own sample and its channel of origin).
+ * Optional outputs x_dev (n, ndim), f_dev (n,), p_dev (n,), ch_dev (n,) int64.
+ * Partials per chunk: stats_partials_dev (n_chunks, 3) = (count, mean, M2) of f/p;
+ * ch_partials_dev (n_chunks, 2*n_channels) = per-channel counts, then per-channel sums of
+ * (f/p)^2 (importance.py:166-167).  chunk must be a multiple of 128. */
+int hepmc_multichannel_sample(const hepmc_density_t* dens, const double* channel_table_dev, int n_channels, int ndim,
+                              int64_t n, int64_t first_index, int64_t chunk, uint64_t seed, uint32_t stream_id,
+                              const double* xs_replay_dev, const int64_t* ch_replay_dev,
+                              double* x_dev, double* f_dev, double* p_dev, int64_t* ch_dev,
+                              double* stats_partials_dev, double* ch_partials_dev, void* stream);
+/* two-kernel path: user integrand values f, mixture densities p, channel ids -> the same partials */
+int hepmc_multichannel_accumulate(const double* f_dev, const double* p_dev, const int64_t* ch_dev, int n_channels,
+                                  int64_t n, int64_t chunk, double* stats_partials_dev, double* ch_partials_dev,
+                                  void* stream);
 
 /* ---- RAMBO: replaces phase_space.Rambo.map (rambo.py:38-69,162-173) ---------------- */
 /* out_dev (n, 4*nparticles) as [E,px,py,pz] per particle.  Native RNG (point index

@@ -471,6 +471,49 @@ def gen_ks_reference():
     save("camel2d_reference_hist", **out)
 
 
+def gen_multichannel(h):
+    """MultiChannelMC (importance.py:54-230) with two Gaussian channels and a uniform one."""
+    from hepmc.core.integration import multi_channel as mcm
+    out = {}
+    np.random.seed(SEED)
+    D = h.densities
+    chans = [D.Gaussian(2, mu=1 / 3, scale=0.1), D.Gaussian(2, mu=[0.6, 0.7], scale=[0.15, 0.1]), D.Uniform(2)]
+    mc = h.MultiChannel(chans)
+    tapes, alphas = [], []
+    orig = mcm.MultiChannel.rvs
+
+    def rvs(self, sample_size, return_sizes=False):
+        pts, sizes = orig(self, sample_size, True)
+        tapes.append((pts.copy(), sizes.copy()))
+        alphas.append(self.channels_weight.copy())
+        return (pts, sizes) if return_sizes else pts
+    mcm.MultiChannel.rvs = rvs
+    try:
+        s = h.MultiChannelMC(mc, b=0.5)(D.Camel(2), [400, 400], [500, 500, 500], [600])
+    finally:
+        mcm.MultiChannel.rvs = orig
+    for j, (pts, sizes) in enumerate(tapes):
+        out["xs_%d" % j] = pts
+        out["sizes_%d" % j] = sizes.astype(np.int64)
+        out["alpha_%d" % j] = alphas[j]
+    out["alpha_final"] = mc.channels_weight.copy()
+    out["n_iter"] = np.array([2, 3, 1])
+    out["integral"] = s.integral
+    out["err"] = s.integral_err
+    out["data"] = s.data
+    out["f"] = s.function_values
+    out["w"] = s.weights
+    out["chan_mu1"] = np.array([0.6, 0.7])
+    out["chan_cov1"] = np.array([0.15, 0.1]) ** 2
+    # MultiChannel.pdf on fixed points with fixed weights
+    rng = np.random.default_rng(SEED)
+    xs = points(64, 2, rng)
+    mc2 = h.MultiChannel(chans, np.array([0.2, 0.5, 0.3]))
+    out["pdf_xs"] = xs
+    out["pdf"] = mc2.pdf(xs)
+    save("multichannel", **out)
+
+
 def gen_importance_ideal(h):
     """tests/test_integration.py:44-52 -- the reference's only exact KAT."""
     np.random.seed(SEED)
@@ -492,6 +535,7 @@ def main():
     gen_metropolis(h)
     gen_elm_and_hmc(h)
     gen_importance_ideal(h)
+    gen_multichannel(h)
     gen_ks_reference()
 
 

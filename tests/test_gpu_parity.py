@@ -259,6 +259,77 @@ def test_importance_reference_unit_tests():
     assert mean == 0.5 and m2 == 0.0
 
 
+# ------------------------------------------------------------------ multi-channel MC ("next" row 1)
+def _mc_setup(g):
+    chans = [H.densities.Gaussian(2, mu=1 / 3, scale=0.1),
+             H.densities.Gaussian(2, mu=g["chan_mu1"], cov=g["chan_cov1"]), H.densities.Uniform(2)]
+    return H.MultiChannel(chans)
+
+
+def test_multichannel_replay():
+    """The kernels consume the reference's own channel samples; weights trajectory, estimates
+    and the final result must match MultiChannelMC of the reference."""
+    g = G("multichannel")
+    mc = _mc_setup(g)
+    n1, n2, n3 = [int(v) for v in g["n_iter"]]
+    tapes = []
+    for j in range(n1 + n2 + n3):
+        sizes = g["sizes_%d" % j]
+        tapes.append((g["xs_%d" % j], np.repeat(np.arange(3), sizes)))
+    mmc = H.MultiChannelMC(mc, b=0.5)
+    counts = [g["xs_%d" % j].shape[0] for j in range(n1 + n2 + n3)]
+    s = mmc(H.densities.Camel(2), counts[:n1], counts[n1:n1 + n2], counts[n1 + n2:], replay=tapes)
+    assert_close(s.integral, g["integral"], RTOL)
+    assert_close(s.integral_err, g["err"], 1e-11)
+    assert_close(mc.channels_weight, g["alpha_final"], RTOL)
+    assert_close(s.data, g["data"], RTOL)
+    assert_close(s.function_values, g["f"], RTOL)
+    assert_close(s.weights, g["w"], RTOL)
+    mc2 = H.MultiChannel(mc.channels, np.array([0.2, 0.5, 0.3]))
+    assert_close(mc2.pdf(g["pdf_xs"]), g["pdf"], RTOL)
+
+
+def test_multichannel_native():
+    g = G("multichannel")
+    H.seed(21)
+    mc = _mc_setup(g)
+    s = H.MultiChannelMC(mc)(H.densities.Camel(2), [20000] * 3, [50000] * 4, [50000], keep_samples=False)
+    assert abs(s.integral - 1.0) < 4 * s.integral_err and s.integral_err < 0.01
+    assert mc.channels_weight[2] < 0.2 and abs(mc.channels_weight.sum() - 1) < 1e-12   # uniform channel suppressed
+    # native draws checked against the oracle with the same Philox words (one iteration, fixed weights)
+    H.seed(22)
+    mc = _mc_setup(g)
+    mc.channels_weight[:] = [0.3, 0.5, 0.2]
+    n = 4000
+    xs, f, p, est, w_est = H.MultiChannelMC(mc).iterate(H.densities.Camel(2), n, update_weights=False)
+    w = O.philox_words(22, 0, np.arange(n), 2)
+    uc = O.u52(w[:, 0, 0], w[:, 0, 1])
+    ch = np.minimum(np.searchsorted(np.cumsum([0.3, 0.5, 0.2]), uc, side="right"), 2)
+    z0, z1 = O.box_muller(O.u52(w[:, 1, 0], w[:, 1, 1]), O.u52(w[:, 1, 2], w[:, 1, 3]))
+    u0, u1 = O.u52(w[:, 1, 0], w[:, 1, 1]), O.u52(w[:, 1, 2], w[:, 1, 3])
+    mu = [np.array([1 / 3, 1 / 3]), g["chan_mu1"]]
+    sc = [np.array([0.1, 0.1]), np.sqrt(g["chan_cov1"])]
+    pts = np.empty((n, 2))
+    for c in (0, 1):
+        m = ch == c
+        pts[m, 0] = mu[c][0] + sc[c][0] * z0[m]
+        pts[m, 1] = mu[c][1] + sc[c][1] * z1[m]
+    m = ch == 2
+    pts[m, 0], pts[m, 1] = u0[m], u1[m]
+    order = np.argsort(ch, kind="stable")
+    assert_close(xs, pts[order], 1e-11, atol=1e-12)
+    chans = [("gauss", 1 / 3, 0.01), ("gauss", g["chan_mu1"], g["chan_cov1"]), ("uniform", 0., 1.)]
+    e_ref, w_ref, _, _ = O.multichannel_iterate(O.camel_pdf, chans, [0.3, 0.5, 0.2], pts[order], np.bincount(ch, minlength=3), update_weights=False)
+    assert_close(est, e_ref, 1e-11)
+    assert_close(w_est, w_ref, 1e-11)
+    # reference unit test tests/test_integration.py:57-63 + user integrand path + ChannelsSample
+    H.seed(23)
+    s = H.MultiChannelMC(H.MultiChannel([H.densities.Uniform(1)]))(lambda x: x, [], [100], [])
+    assert abs(s.integral - 0.5) < 0.2 and s.integral_err < 0.1
+    cs = mc.sample(1000)
+    assert cs.data.shape == (1000, 2) and cs.count_per_channel.sum() == 1000 and cs.weights.shape == (1000,)
+
+
 # ------------------------------------------------------------------ RAMBO
 @pytest.mark.parametrize("tag,e_cm,npart", [("4_100", 100., 4), ("3_50", 50., 3), ("6_1000", 1000., 6), ("2_10", 10., 2)])
 def test_rambo_replay(tag, e_cm, npart):

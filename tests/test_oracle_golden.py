@@ -165,6 +165,22 @@ def test_hmc(tag):
     assert_close(chain, g[tag + "_chain"], 1e-9, atol=1e-9)
 
 
+def _mc_channels(g):
+    return [("gauss", 1 / 3, 0.01), ("gauss", g["chan_mu1"], g["chan_cov1"]), ("uniform", 0., 1.)]
+
+
+def test_multichannel():
+    g = G("multichannel")
+    chans = _mc_channels(g)
+    n1, n2, n3 = [int(v) for v in g["n_iter"]]
+    tapes = [(g["xs_%d" % j], g["sizes_%d" % j]) for j in range(n1 + n2 + n3)]
+    r = O.multichannel_mc(O.camel_pdf, chans, np.ones(3) / 3, tapes, n1, n2, n3)
+    assert_close(r["integral"], g["integral"], 1e-13)
+    assert_close(r["integral_err"], g["err"], 1e-12)
+    assert_close(r["alpha"], g["alpha_final"], 1e-13)
+    assert_close(O.multichannel_pdf(chans, [0.2, 0.5, 0.3], g["pdf_xs"]), g["pdf"], 1e-14)
+
+
 def test_philox_kat():
     """Random123 known-answer vectors for Philox4x32-10."""
     kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
