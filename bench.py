@@ -213,7 +213,9 @@ def run_b200(args):
     achieved = FLOP_PER_POINT * n_local / (kernel_ms * 1e-3) / 1e12
 
     others = {}
-    if rank == 0 and not args.no_others:
+    # the other configs are single-GPU workloads: only in the N = 1 run (under torch.distributed the
+    # library would look for its peers in every reduction)
+    if world == 1 and not args.no_others:
         others = other_workloads(H, _lib, torch, fp64_peak, world == 1 and not args.no_cpu)
 
     if rank != 0:

@@ -29,11 +29,11 @@ __device__ __forceinline__ TcSetup tc_prologue(unsigned char* smem, const hepmc_
     if (warp == MMA_WARP) tmem_alloc(smem_u32(u.s.tmem_ptr), TMEM_COLS);
     if (threadIdx.x == 0) {
         mbar_init(u.bars + 8 * BAR_A, N_OWNER / 32);
-        mbar_init(u.bars + 8 * BAR_S0, 1);
-        mbar_init(u.bars + 8 * BAR_S1, 1);
-        mbar_init(u.bars + 8 * BAR_P0, N_COMPUTE / 32);
-        mbar_init(u.bars + 8 * BAR_P1, N_COMPUTE / 32);
         mbar_init(u.bars + 8 * BAR_D2, 1);
+        for (int b = 0; b < N_SBUF; ++b) {
+            mbar_init(u.bars + 8 * (BAR_S0 + b), 1);
+            mbar_init(u.bars + 8 * (BAR_P0 + b), N_COMPUTE / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     build_tables<D>(u.s, elm.p0_dev, elm.p1_dev, elm.out_w_dev, elm.nodes, u.n_node_tiles);

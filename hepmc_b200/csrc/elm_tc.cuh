@@ -33,8 +33,9 @@ constexpr int TILE_N = 128;      // nodes per tile
 constexpr int K1 = 32;           // 3 * (D + 2) padded to a multiple of 8, D <= 8
 constexpr int N2 = 16;           // D + 1 padded to the MMA N granularity at M = 128
 constexpr int MAX_D = 8;
-constexpr int N_ACC = 1;          // GEMM-2 accumulators (measured: splitting over 4 independent accumulators gains nothing)
-constexpr int COL_A1 = 0, COL_D2 = 32, COL_S0 = 96, COL_S1 = 224, TMEM_COLS = 512;
+constexpr int N_ACC = 1;          // GEMM-2 accumulators (round-robin over 2 or 4 measured: no gain, a tcgen05.mma costs ~100 cycles here)
+constexpr int N_SBUF = 3;         // S/P tiles in flight: the commit -> mbarrier -> waiter round trip is ~1000 cycles
+constexpr int COL_A1 = 0, COL_D2 = 32, COL_S0 = 64, TMEM_COLS = 512;   // S buffer b at COL_S0 + 128 b
 constexpr int B1_TILE_BYTES = (K1 / 4) * TILE_N * 16;   // [K chunk][node row][16 B]
 constexpr int B2_TILE_BYTES = (TILE_N / 4) * N2 * 16;   // [node chunk][n row][16 B]
 constexpr int N_OWNER = TILE_M;                         // owner threads: one chain = one TMEM lane each
@@ -90,6 +91,22 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
         "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Same, descriptor passed as (lo, hi) words and the accumulate flag as a compile-time constant:
+// the issuing thread is a single lane, so every scalar instruction per MMA is ~5 cycles of
+// issue latency -- the descriptor is advanced with ONE 32-bit add per MMA.
+template <int ACC>
+__device__ __forceinline__ void umma_tf32_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi,
+                                                uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 bd;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 bd, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "n"(ACC) : "memory");
 }
 
 #define HEPMC_R8(v, o) "=r"(v[o]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
@@ -167,11 +184,11 @@ __device__ __forceinline__ Shared carve_tc(unsigned char* base, int n_tiles) {
     s.b1 = reinterpret_cast<float*>(base);
     s.b2 = reinterpret_cast<float*>(base + (size_t)n_tiles * B1_TILE_BYTES);
     s.bars = reinterpret_cast<uint64_t*>(base + (size_t)n_tiles * (B1_TILE_BYTES + B2_TILE_BYTES));
-    s.tmem_ptr = reinterpret_cast<uint32_t*>(s.bars + 8);
+    s.tmem_ptr = reinterpret_cast<uint32_t*>(s.bars + 2 + 2 * N_SBUF);
     return s;
 }
 
-enum { BAR_A = 0, BAR_S0 = 1, BAR_S1 = 2, BAR_P0 = 3, BAR_P1 = 4, BAR_D2 = 5 };
+enum { BAR_A = 0, BAR_D2 = 1, BAR_S0 = 2, BAR_P0 = 2 + N_SBUF };   // S_full[b] = BAR_S0 + b, P_ready[b] = BAR_P0 + b
 
 // Build the resident node tables (all threads).  centers (I, D), widths (I,), out_w (I,).
 template <int D>
@@ -230,26 +247,36 @@ __device__ __forceinline__ void build_tables(const Shared& s, const double* __re
 
 // ---- MMA-issuer side: one gradient evaluation over all node tiles (one elected thread) ----
 struct IssuerState {
-    uint32_t ph_a = 0, ph_p0 = 0, ph_p1 = 0;
+    uint32_t ph_a = 0;
+    uint32_t ph_p[N_SBUF] = {};
 };
 
 __device__ __forceinline__ void issue_g1(uint32_t tmem_base, uint32_t b1_saddr, int t, int n_cols) {
-    const uint32_t d = tmem_base + ((t & 1) ? COL_S1 : COL_S0);
+    const uint32_t d = tmem_base + COL_S0 + (t % N_SBUF) * TILE_N;
     const uint32_t idesc = make_idesc(TILE_M, n_cols);
-    const int nks = (g_tc_debug & 8) ? 1 : K1 / 8;
+    const uint64_t bd0 = make_desc(b1_saddr + t * B1_TILE_BYTES, TILE_N * 16, 128);
+    const uint32_t lo = (uint32_t)bd0, hi = (uint32_t)(bd0 >> 32);
+    const uint32_t a = tmem_base + COL_A1;
+    constexpr uint32_t STEP = (2 * TILE_N * 16) >> 4;   // two 16-byte K chunks per MMA, in descriptor units
+    umma_tf32_ts_lh<0>(d, a, lo, hi, idesc);
 #pragma unroll
-    for (int ks = 0; ks < K1 / 8; ++ks) {
-        if (ks >= nks) break;
-        const uint64_t bd = make_desc(b1_saddr + t * B1_TILE_BYTES + ks * 2 * (TILE_N * 16), TILE_N * 16, 128);
-        umma_tf32_ts(d, tmem_base + COL_A1 + ks * 8, bd, idesc, ks > 0 ? 1u : 0u);
-    }
+    for (int ks = 1; ks < K1 / 8; ++ks) umma_tf32_ts_lh<1>(d, a + ks * 8, lo + ks * STEP, hi, idesc);
 }
 __device__ __forceinline__ void issue_g2(uint32_t tmem_base, uint32_t b2_saddr, int t, int n_cols, bool first) {
-    const uint32_t a = tmem_base + ((t & 1) ? COL_S1 : COL_S0);
+    const uint32_t a = tmem_base + COL_S0 + (t % N_SBUF) * TILE_N;
+    const uint32_t d = tmem_base + COL_D2;
     const uint32_t idesc = make_idesc(TILE_M, N2);
-    for (int ks = 0; ks < n_cols / 8; ++ks) {
-        const uint64_t bd = make_desc(b2_saddr + t * B2_TILE_BYTES + ks * 2 * (N2 * 16), N2 * 16, 128);
-        umma_tf32_ts(tmem_base + COL_D2 + (ks % N_ACC) * N2, a + ks * 8, bd, idesc, (first && ks < N_ACC) ? 0u : 1u);
+    const uint64_t bd0 = make_desc(b2_saddr + t * B2_TILE_BYTES, N2 * 16, 128);
+    const uint32_t lo = (uint32_t)bd0, hi = (uint32_t)(bd0 >> 32);
+    constexpr uint32_t STEP = (2 * N2 * 16) >> 4;
+    const int nk = n_cols >> 3;
+#pragma unroll
+    for (int ks = 0; ks < TILE_N / 8; ++ks) {
+        if (ks < nk) {
+            const uint32_t dq = d + (ks % N_ACC) * N2;
+            if (first && ks < N_ACC) umma_tf32_ts_lh<0>(dq, a + ks * 8, lo + ks * STEP, hi, idesc);
+            else umma_tf32_ts_lh<1>(dq, a + ks * 8, lo + ks * STEP, hi, idesc);
+        }
     }
 }
 
@@ -264,20 +291,22 @@ __device__ __forceinline__ void issuer_eval(IssuerState& st, uint32_t bars, uint
     mbar_wait(bars + 8 * BAR_A, st.ph_a);
     st.ph_a ^= 1;
     fence_after();
-    issue_g1(tmem_base, b1_saddr, 0, tile_cols(nodes, 0));
-    umma_commit(bars + 8 * BAR_S0);
-    if (n_tiles > 1) {
-        issue_g1(tmem_base, b1_saddr, 1, tile_cols(nodes, 1));
-        umma_commit(bars + 8 * BAR_S1);
+#pragma unroll
+    for (int b = 0; b < N_SBUF; ++b) {
+        if (b < n_tiles) {
+            issue_g1(tmem_base, b1_saddr, b, tile_cols(nodes, b));
+            umma_commit(bars + 8 * (BAR_S0 + b));
+        }
     }
     for (int t = 0; t < n_tiles; ++t) {
-        if (t & 1) { mbar_wait(bars + 8 * BAR_P1, st.ph_p1); st.ph_p1 ^= 1; }
-        else { mbar_wait(bars + 8 * BAR_P0, st.ph_p0); st.ph_p0 ^= 1; }
+        const int b = t % N_SBUF;
+        mbar_wait(bars + 8 * (BAR_P0 + b), st.ph_p[b]);
+        st.ph_p[b] ^= 1;
         fence_after();
-        if (!(g_tc_debug & 1)) issue_g2(tmem_base, b2_saddr, t, (g_tc_debug & 4) ? 8 : tile_cols(nodes, t), t == 0);
-        if (t + 2 < n_tiles) {
-            issue_g1(tmem_base, b1_saddr, t + 2, tile_cols(nodes, t + 2));
-            umma_commit(bars + 8 * ((t & 1) ? BAR_S1 : BAR_S0));
+        if (!(g_tc_debug & 1)) issue_g2(tmem_base, b2_saddr, t, tile_cols(nodes, t), t == 0);
+        if (t + N_SBUF < n_tiles) {
+            issue_g1(tmem_base, b1_saddr, t + N_SBUF, tile_cols(nodes, t + N_SBUF));
+            umma_commit(bars + 8 * (BAR_S0 + b));
         }
     }
     umma_commit(bars + 8 * BAR_D2);
@@ -285,7 +314,8 @@ __device__ __forceinline__ void issuer_eval(IssuerState& st, uint32_t bars, uint
 
 // ---- compute side: thread = chain = TMEM lane ----
 struct ComputeState {
-    uint32_t ph_s0 = 0, ph_s1 = 0, ph_d2 = 0;
+    uint32_t ph_s[N_SBUF] = {};
+    uint32_t ph_d2 = 0;
 };
 
 // S -> P = exp2(S) in place for one half (64 columns) of every node tile of one gradient
@@ -293,9 +323,10 @@ struct ComputeState {
 __device__ __forceinline__ void exp_half_tiles(ComputeState& st, uint32_t bars, uint32_t tmem_lane_base, int nodes,
                                                int n_tiles, int half) {
     for (int t = 0; t < n_tiles; ++t) {
-        const uint32_t col = ((t & 1) ? COL_S1 : COL_S0) + half * 64;
-        if (t & 1) { mbar_wait(bars + 8 * BAR_S1, st.ph_s1); st.ph_s1 ^= 1; }
-        else { mbar_wait(bars + 8 * BAR_S0, st.ph_s0); st.ph_s0 ^= 1; }
+        const int b = t % N_SBUF;
+        const uint32_t col = COL_S0 + b * TILE_N + half * 64;
+        mbar_wait(bars + 8 * (BAR_S0 + b), st.ph_s[b]);
+        st.ph_s[b] ^= 1;
         fence_after();
         const int my_cols = tile_cols(nodes, t) - half * 64;   // columns of this half that GEMM-2 reads
         if (my_cols > 0 && !(g_tc_debug & 2)) {
@@ -303,6 +334,15 @@ __device__ __forceinline__ void exp_half_tiles(ComputeState& st, uint32_t bars, 
             // while the MUFU works on chunk c (TMEM read and MUFU both run at 4 values/clk/SMSP)
             const int nch = my_cols >= 64 ? 4 : (my_cols >> 4);
             uint32_t va[16], vb[16];
+            if (g_tc_debug & 16) {  // experiment: MUFU work without touching TMEM
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { va[j] = threadIdx.x + j; vb[j] = threadIdx.x * 3 + j; }
+                for (int c = 0; c < nch; ++c) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) va[j] = __float_as_uint(ex2_approx(__uint_as_float(va[j] ^ vb[j])));
+                }
+                if (va[3] == 0x12345u) tmem_st16(tmem_lane_base + col, va);
+            } else {
             tmem_ld16(tmem_lane_base + col, va);
             tmem_wait_ld();
 #pragma unroll
@@ -322,11 +362,12 @@ __device__ __forceinline__ void exp_half_tiles(ComputeState& st, uint32_t bars, 
                     if (c + 1 < nch) tmem_wait_ld();
                 }
             }
+            }
             tmem_wait_st();
         }
         fence_before();
         __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(bars + 8 * ((t & 1) ? BAR_P1 : BAR_P0));  // one arrival per warp
+        if ((threadIdx.x & 31) == 0) mbar_arrive(bars + 8 * (BAR_P0 + b));  // one arrival per warp
     }
 }
 
@@ -378,20 +419,19 @@ __device__ __forceinline__ void compute_eval(ComputeState& st, uint32_t bars, ui
     mbar_wait(bars + 8 * BAR_D2, st.ph_d2);
     st.ph_d2 ^= 1;
     fence_after();
+    uint32_t d2[N_ACC][16];
+#pragma unroll
+    for (int q = 0; q < N_ACC; ++q) tmem_ld16(tmem_lane_base + COL_D2 + q * N2, d2[q]);
+    tmem_wait_ld();
     float acc[D + 1];
 #pragma unroll
-    for (int k = 0; k <= D; ++k) acc[k] = 0.f;
+    for (int k = 0; k <= D; ++k) {
+        acc[k] = __uint_as_float(d2[0][k]);
 #pragma unroll
-    for (int q = 0; q < N_ACC; ++q) {
-        uint32_t d2[16];
-        tmem_ld16(tmem_lane_base + COL_D2 + q * N2, d2);
-        tmem_wait_ld();
-#pragma unroll
-        for (int k = 0; k <= D; ++k) acc[k] += __uint_as_float(d2[k]);
+        for (int q = 1; q < N_ACC; ++q) acc[k] += __uint_as_float(d2[q][k]);
     }
-    const float sum = acc[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) g[k] = (double)(acc[k] - xc[k] * sum);
+    for (int k = 0; k < D; ++k) g[k] = (double)(acc[k] - xc[k] * acc[D]);
 }
 
 }  // namespace tc
