@@ -23,5 +23,6 @@ from .core.sampling import Sample
 from .core.density import Proposal, Density, Distribution
 from . import hamiltonian
 from . import surrogate
+from . import mc3
 
 __version__ = "0.1.0"

@@ -75,6 +75,8 @@ SIGNATURES = {
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hepmc_hmc_chains": (_int, [_dens_p, _elm_p, _int, _vp, ctypes.POINTER(_dbl), _dbl, _int,
                                 _i64, _i64, _i64, _i64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hepmc_mc3_chains": (_int, [_dens_p, _vp, _int, _dbl, _int, ctypes.POINTER(_dbl), _dbl, _int, _elm_p, _int, _vp,
+                                _i64, _i64, _i64, _i64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hepmc_elm_eval": (_int, [_elm_p, _int, _int, _int, _vp, _i64, _vp, _vp]),
 }
 

@@ -57,6 +57,11 @@ class DefaultMetropolis(MetropolisUpdate):
             raise ValueError('target must have dimension ' + str(self.ndim))
         if self.is_adaptive:
             raise TypeError("adaptive Metropolis mutates shared state per step: out of scope")
+        from ..integration.multi_channel import MultiChannel
+        if isinstance(self._proposal, MultiChannel):
+            # importance-sampling Metropolis-Hastings: the (MC)^3 kernel with beta = 1
+            from .mixing import run_mc3
+            return run_mc3(dens, self._proposal, 1.0, None, x0, sample_size, thin, store_chain, first_chain, replay)
         kind, params = self._proposal_params()
         return ensemble.run_rwm(dens._block(), x0, kind, params, sample_size, thin, store_chain,
                                 first_chain, None, replay)

@@ -1,0 +1,3 @@
+from .mc3 import BasicMC3, MC3Hamilton
+
+__all__ = ['BasicMC3', 'MC3Hamilton']

@@ -261,6 +261,27 @@ int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int pr
                      double* chain_dev, double* last_dev, int64_t* accepted_dev,
                      int64_t* total_accepted_dev, void* stream);
 
+/* ---- (MC)^3 mixing chains ("next" row 3): replaces MixingMarkovUpdate.next_state
+ * (core/markov/base.py:139-179) over [DefaultMetropolis(target, MultiChannel) , local update],
+ * i.e. the sampler mc3.BasicMC3 / interfaces/mc3_hmc*.py build ------------------------------ */
+/* Per step and chain: with probability beta an importance-sampling Metropolis-Hastings update
+ * (candidate drawn from the channel mixture, Hastings ratio pdf(c) q(x) / (pdf(x) q(c)),
+ * metropolis.py:46-47), otherwise the local update: local_kind 0 = Gaussian random walk with
+ * diag covariance local_scale_host[ndim]; local_kind 1 = HMC with diag mass local_scale_host[ndim],
+ * step_size, steps and the exact or ELM-surrogate gradient (elm may be NULL; precision 0/1).
+ * channel_table_dev as in hepmc_multichannel_sample.  Replay tapes (all three or none):
+ * sel_replay_dev (C, T-1) int64 (0 = IS update, 1 = local), draw_replay_dev (C, T-1, ndim) = the
+ * candidate (IS) / standard normals (random walk) / momentum (HMC), u_replay_dev (C, T-1).
+ * Outputs as hepmc_rwm_chains. */
+int hepmc_mc3_chains(const hepmc_density_t* dens, const double* channel_table_dev, int n_channels, double beta,
+                     int local_kind, const double* local_scale_host, double step_size, int steps,
+                     const hepmc_elm_t* elm, int precision, const double* x0_dev,
+                     int64_t n_chains, int64_t first_chain, int64_t sample_size, int64_t thin,
+                     uint64_t seed, uint32_t stream_id,
+                     const int64_t* sel_replay_dev, const double* draw_replay_dev, const double* u_replay_dev,
+                     double* chain_dev, double* last_dev, int64_t* accepted_dev, int64_t* total_accepted_dev,
+                     void* stream);
+
 /* ---- ELM surrogate: replaces FunctionBasis.eval (extreme_learning.py:18-29),
  * RadialBasis.output_matrix/eval_gradient (:190-207,222-230), AdditiveBasis.* (:120-146) */
 /* xs_dev (n, ndim).  what: 0 = eval -> (n,), 1 = eval_gradient -> (n, ndim),

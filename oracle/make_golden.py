@@ -514,6 +514,86 @@ def gen_multichannel(h):
     save("multichannel", **out)
 
 
+def gen_mixing(h):
+    """MixingMarkovUpdate([IS-Metropolis over a MultiChannel, local update]) -- the MC3 sampler
+    (base.py:139-179, interfaces/mc3_hmc.py).  Tapes: selector, candidate / momentum / normals, u."""
+    out = {}
+    D = h.densities
+    T = 300
+    weights = np.array([0.4, 0.4, 0.2])
+    for tag in ("hmc", "rwm"):
+        np.random.seed(SEED + (1 if tag == "rwm" else 0))
+        target = D.Camel(2)
+        channels = h.MultiChannel([D.Gaussian(2, mu=1 / 3, scale=0.1), D.Gaussian(2, mu=2 / 3, scale=0.1), D.Uniform(2)],
+                                  weights.copy())
+        is_upd = h.DefaultMetropolis(2, target, channels)
+        if tag == "hmc":
+            local = h.hamiltonian.HamiltonianUpdate(target, D.Gaussian(2, cov=1.), 10, 0.02)
+            local_var = np.array([1., 1.])
+        else:
+            local = h.DefaultMetropolis(2, target, h.proposals.Gaussian(2, cov=np.diag([0.002, 0.003])))
+            local_var = np.array([0.002, 0.003])
+        mix = h.MixingMarkovUpdate(2, [is_upd, local], [0.4, 0.6])
+        x0s = [np.array([0.3, 0.35]), np.array([0.7, 0.6])]
+        chains, accs, sels, draws, us = [], [], [], [], []
+        for x0 in x0s:
+            log = {"sel": [], "cand": None, "p": None, "z": None}
+            steps_log = []
+            orig_choice = np.random.choice
+            np.random.choice = lambda *a, **k: (lambda v: (log["sel"].append(int(v)), v)[1])(orig_choice(*a, **k))
+            orig_rvs = channels.rvs
+            def rvs(n, return_sizes=False, _o=orig_rvs):
+                r = _o(n, return_sizes)
+                if n == 1 and not return_sizes:
+                    log["cand"] = np.array(r[0], copy=True)
+                return r
+            channels.rvs = rvs
+            if tag == "hmc":
+                orig_pp = local.p_dist.proposal
+                def pprop(state=None, _o=orig_pp):
+                    v = _o(state)
+                    log["p"] = np.array(v, copy=True)
+                    return v
+                local.p_dist.proposal = pprop
+            with Tape() as tp:
+                orig_next = mix.next_state
+                def next_state(state, it, _o=orig_next):
+                    nz, nu = len(tp.log["z"]), len(tp.log["rand"])
+                    out_state = _o(state, it)
+                    sel = log["sel"][-1]
+                    if sel == 0:
+                        dr = log["cand"]
+                    elif tag == "hmc":
+                        dr = log["p"]
+                    else:
+                        dr = np.ravel(tp.log["z"][-1])
+                    nunif = len(tp.log["rand"]) - nu
+                    assert nunif in (0, 1)
+                    steps_log.append((sel, np.array(dr, copy=True), float(tp.log["rand"][-1]) if nunif else np.nan))
+                    return out_state
+                mix.next_state = next_state
+                smp = mix.sample(T, x0, log_every=-1)
+                mix.next_state = orig_next
+            np.random.choice = orig_choice
+            channels.rvs = orig_rvs
+            if tag == "hmc":
+                local.p_dist.proposal = orig_pp
+            chains.append(smp.data)
+            accs.append(smp.accepted)
+            sels.append([s_[0] for s_ in steps_log])
+            draws.append(np.stack([s_[1] for s_ in steps_log]))
+            us.append([s_[2] for s_ in steps_log])
+        out[tag + "_x0"] = np.stack(x0s)
+        out[tag + "_chain"] = np.stack(chains)
+        out[tag + "_accepted"] = np.array(accs, dtype=np.int64)
+        out[tag + "_sel"] = np.array(sels, dtype=np.int64)
+        out[tag + "_draw"] = np.stack(draws)
+        out[tag + "_u"] = np.array(us)
+        out[tag + "_local_var"] = local_var
+    out["weights"] = weights
+    save("mixing", **out)
+
+
 def gen_importance_ideal(h):
     """tests/test_integration.py:44-52 -- the reference's only exact KAT."""
     np.random.seed(SEED)
@@ -536,6 +616,7 @@ def main():
     gen_elm_and_hmc(h)
     gen_importance_ideal(h)
     gen_multichannel(h)
+    gen_mixing(h)
     gen_ks_reference()
 
 

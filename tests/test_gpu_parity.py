@@ -463,6 +463,62 @@ def test_metropolis_ks_against_reference_sample():
     assert abs(pts.mean() - 0.5) < 0.01 and abs(pts.var(axis=0).mean() - float(g["var"].mean())) < 0.003
 
 
+# ------------------------------------------------------------------ (MC)^3 mixing chains ("next" row 3)
+def _mixing_setup(tag, weights):
+    target = H.densities.Camel(2)
+    channels = H.MultiChannel([H.densities.Gaussian(2, mu=1 / 3, scale=0.1), H.densities.Gaussian(2, mu=2 / 3, scale=0.1),
+                               H.densities.Uniform(2)], np.array(weights, dtype=np.float64))
+    is_upd = H.DefaultMetropolis(2, target, channels)
+    if tag == "hmc":
+        local = H.hamiltonian.HamiltonianUpdate(target, H.densities.Gaussian(2, cov=1.), 10, 0.02)
+    else:
+        local = H.DefaultMetropolis(2, target, H.proposals.Gaussian(2, cov=np.diag([0.002, 0.003])))
+    return target, channels, is_upd, local
+
+
+@pytest.mark.parametrize("tag", ["hmc", "rwm"])
+def test_mixing_replay(tag):
+    g = G("mixing")
+    target, channels, is_upd, local = _mixing_setup(tag, g["weights"])
+    assert is_upd.is_hasting                                  # reference tests/test_mc3.py:20
+    mix = H.MixingMarkovUpdate(2, [is_upd, local], [0.4, 0.6])
+    T = g[tag + "_chain"].shape[1]
+    s = mix.sample(T, g[tag + "_x0"], replay=(g[tag + "_sel"], g[tag + "_draw"], _fill(g[tag + "_u"])))
+    assert np.array_equal(s.accepted, g[tag + "_accepted"])
+    assert_close(s.data, g[tag + "_chain"], 1e-9, atol=1e-11)
+
+
+def test_mixing_native_and_mc3():
+    from oracle.stats_oracle import ks
+    g = G("camel2d_reference_hist")
+    H.seed(404)
+    target, channels, is_upd, local = _mixing_setup("hmc", [0.4, 0.4, 0.2])
+    mix = H.MixingMarkovUpdate(2, [is_upd, local], [0.5, 0.5])
+    C, T = 20000, 200
+    x0 = np.tile([0.3, 0.35], (C, 1))
+    s = mix.sample(T, x0, store_chain=False)
+    pts = s.data[:, 0]
+    hist, _ = np.histogramdd(pts, bins=[g["edges"][0], g["edges"][1]])
+    res = np.array(ks(hist, g["truth"]))
+    assert np.all(res[:, 0] < res[:, 1]), res                  # KS vs the 1M reference sample
+    assert 0.2 < s.accepted.mean() / T < 0.95
+    # pure importance-sampling Metropolis (beta = 1): DefaultMetropolis with a MultiChannel proposal
+    H.seed(405)
+    s1 = is_upd.sample(T, x0, store_chain=False)
+    hist, _ = np.histogramdd(s1.data[:, 0], bins=[g["edges"][0], g["edges"][1]])
+    res = np.array(ks(hist, g["truth"]))
+    assert np.all(res[:, 0] < res[:, 1]), res
+    # MC3Hamilton: integrate (adapts the channel weights) then sample; reference tests/test_mc3.py shapes
+    H.seed(406)
+    mc3 = H.mc3.MC3Hamilton(H.densities.Camel(2), H.MultiChannel([H.densities.Gaussian(2, mu=1 / 3, scale=0.1),
+                            H.densities.Gaussian(2, mu=2 / 3, scale=0.1), H.densities.Uniform(2)]), np.ones(2), 10, 0.02, beta=0.5)
+    res = mc3(([], [2000] * 5, []), 300, initial=[0.3, 0.35])
+    assert res.data.shape == (300, 2) and abs(mc3.integration_sample.integral - 1.0) < 0.1
+    assert mc3.channels.channels_weight[2] < 0.25
+    res = mc3.sample(50)
+    assert res.data.shape == (50, 2)
+
+
 # ------------------------------------------------------------------ ELM + HMC
 def _elm(tag="g100"):
     e = G("elm")

@@ -181,6 +181,17 @@ def test_multichannel():
     assert_close(O.multichannel_pdf(chans, [0.2, 0.5, 0.3], g["pdf_xs"]), g["pdf"], 1e-14)
 
 
+@pytest.mark.parametrize("tag,kind", [("hmc", 1), ("rwm", 0)])
+def test_mixing_chains(tag, kind):
+    g = G("mixing")
+    chans = [("gauss", 1 / 3, 0.01), ("gauss", 2 / 3, 0.01), ("uniform", 0., 1.)]
+    chain, acc = O.mixing_chains(O.camel_pdf, chans, g["weights"], kind, g[tag + "_local_var"], g[tag + "_x0"],
+                                 g[tag + "_sel"], g[tag + "_draw"], _fill(g[tag + "_u"]),
+                                 pot_grad_fn=O.camel_pot_gradient, step_size=0.02, steps=10)
+    assert np.array_equal(acc, g[tag + "_accepted"])
+    assert_close(chain, g[tag + "_chain"], 1e-10, atol=1e-12)
+
+
 def test_philox_kat():
     """Random123 known-answer vectors for Philox4x32-10."""
     kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
