@@ -19,7 +19,7 @@ from .core import phase_space
 from .core.integration import *
 from .core.markov import *
 
-from .core.sampling import Sample
+from .core.sampling import Sample, AcceptRejectSampler
 from .core.density import Proposal, Density, Distribution
 from . import hamiltonian
 from . import surrogate

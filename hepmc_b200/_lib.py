@@ -70,6 +70,9 @@ SIGNATURES = {
                                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hepmc_multichannel_accumulate": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _vp, _vp, _vp]),
     "hepmc_rambo_map": (_int, [_int, _dbl, _i64, _i64, _u64, _u32, _vp, _vp, _vp]),
+    "hepmc_rambo_diet_map": (_int, [_int, _dbl, _i64, _i64, _u64, _u32, _vp, _vp, _vp]),
+    "hepmc_rambo_diet_inverse": (_int, [_int, _dbl, _i64, _vp, _vp, _vp]),
+    "hepmc_accept_flags": (_int, [_vp, _vp, _dbl, _dbl, _i64, _i64, _u64, _u32, _vp, _vp]),
     "hepmc_rambo_pdf": (_dbl, [_int, _dbl]),
     "hepmc_rwm_chains": (_int, [_dens_p, _vp, _int, ctypes.POINTER(_dbl), _i64, _i64, _i64, _i64, _u64, _u32,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -6,5 +6,5 @@ from . import phase_space
 from .integration import *
 from .markov import *
 
-from .sampling import Sample
+from .sampling import Sample, AcceptRejectSampler
 from .density import Proposal, Density, Distribution

@@ -2,6 +2,6 @@ from .gaussian import Gaussian
 from .camel import Camel, UnconstrainedCamel
 from .uniform import Uniform
 from .banana import Banana
-from .rambo import Rambo
+from .rambo import Rambo, RamboOnDiet
 
-__all__ = ['Gaussian', 'Camel', 'UnconstrainedCamel', 'Uniform', 'Banana', 'Rambo']
+__all__ = ['Gaussian', 'Camel', 'UnconstrainedCamel', 'Uniform', 'Banana', 'Rambo', 'RamboOnDiet']

@@ -37,3 +37,36 @@ class Rambo(Distribution):
     @nparticles.setter
     def nparticles(self, value):
         self.mapping = phase_space.Rambo(self.e_cm, value)
+
+
+class RamboOnDiet(Distribution):
+    """Distribution wrapper of the RamboOnDiet mapping (densities/rambo.py:36-63)."""
+
+    def __init__(self, nparticles, E_CM):
+        self.mapping = phase_space.RamboOnDiet(E_CM, nparticles)
+        super().__init__(self.mapping.ndim, False)
+
+    def rvs(self, sample_size):
+        from ... import _lib
+        n = int(sample_size)
+        first, count, _ = parallel.local_span(n, _lib.default_chunk(n))
+        return config.deliver(self.mapping.generate(count, first_index=first))
+
+    def pdf(self, xs):
+        return self.mapping.pdf(xs)
+
+    @property
+    def e_cm(self):
+        return self.mapping.e_cm
+
+    @e_cm.setter
+    def e_cm(self, value):
+        self.mapping.e_cm = value
+
+    @property
+    def nparticles(self):
+        return self.mapping.nparticles
+
+    @nparticles.setter
+    def nparticles(self, value):
+        self.mapping = phase_space.RamboOnDiet(self.e_cm, value)

@@ -1,3 +1,4 @@
-from .rambo import Rambo, PhaseSpaceMapping
+from .rambo import Rambo, RamboOnDiet, PhaseSpaceMapping
+from .mapping import MappedDensity
 
-__all__ = ['Rambo', 'PhaseSpaceMapping']
+__all__ = ['Rambo', 'RamboOnDiet', 'MappedDensity', 'PhaseSpaceMapping']

@@ -104,3 +104,55 @@ class Sample(object):
     def __repr__(self):
         return (type(self).__name__ + '\n\t' + '\n\t'.join(
             '%s: %s' % (t, e) for t, e in zip(*self._data_table())))
+
+
+class AcceptRejectSampler(object):
+    """Acceptance-rejection sampling (mirror of hepmc/core/sampling.py:149-204): proposals
+    x ~ sampling_pdf are kept when  u * bound * sampling_pdf(x) <= pdf(x).  Proposals, the
+    acceptance test (hepmc_accept_flags) and the compaction run on the device; pdf / sampling /
+    sampling_pdf follow the integrand convention (ndim arrays in, one array out; built-in
+    densities are evaluated by their kernels, other callables receive CUDA tensors)."""
+
+    def __init__(self, pdf, bound, ndim=1, sampling=None, sampling_pdf=None):
+        self.pdf = pdf
+        self.c = bound
+        self.ndim = ndim
+        self.sampling = sampling
+        self.sampling_pdf = sampling_pdf
+
+    def sample(self, sample_size, batch=None):
+        import ctypes
+        from .. import _lib, rng, config
+        from .integration import engine
+        from .density import as_builtin
+        dev = _lib.device()
+        sample_size = int(sample_size)
+        x = torch.empty((sample_size, self.ndim), dtype=torch.float64, device=dev)
+        filled = 0
+        dens = as_builtin(self.pdf)
+        seed = rng.get_seed()
+        while filled < sample_size:
+            need = sample_size - filled
+            m = int(batch) if batch else max(1024, 2 * need)
+            if self.sampling is None:
+                prop = engine.uniform_rvs(m, self.ndim)
+                q, q_scalar = None, 1.0
+            else:
+                prop, _ = _lib.to_device(self.sampling(m))
+                prop = prop.reshape(m, self.ndim).contiguous()
+                qv = self.sampling_pdf(*[prop[:, d] for d in range(self.ndim)])
+                if isinstance(qv, (int, float)):
+                    q, q_scalar = None, float(qv)
+                else:
+                    q, q_scalar = _lib.to_device(qv)[0].reshape(-1).contiguous(), 1.0
+            if dens is not None:
+                f = dens.pdf(prop)
+            else:
+                f = engine.call_integrand(self.pdf, [prop[:, d] for d in range(self.ndim)])
+            flags = torch.empty(m, dtype=torch.uint8, device=dev)
+            _lib.call("hepmc_accept_flags", _lib.ptr(f), _lib.ptr(q), q_scalar, float(self.c), m, 0, seed,
+                      rng.next_stream(), _lib.ptr(flags), _lib.stream_ptr())
+            keep = prop[flags.bool()][:need]
+            x[filled:filled + keep.shape[0]] = keep
+            filled += keep.shape[0]
+        return Sample(data=config.deliver(x), target=self.pdf)

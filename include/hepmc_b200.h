@@ -208,6 +208,21 @@ int hepmc_rambo_map(int nparticles, double e_cm, int64_t n, int64_t first_index,
 /* Rambo.pdf (rambo.py:28-36): the constant 1/Phi_n, computed on the host. */
 double hepmc_rambo_pdf(int nparticles, double e_cm);
 
+/* ---- RamboOnDiet + accept/reject ("next" row 4): phase_space.RamboOnDiet.map / map_inverse
+ * (core/phase_space/rambo.py:72-149, boost :180-189) and the acceptance test of
+ * AcceptRejectSampler.sample (core/sampling.py:196-201) ------------------------------------- */
+/* map: xs (n, 3*nparticles-4) unit-cube points (native RNG when xs_replay_dev is NULL) ->
+ * out_dev (n, 4*nparticles).  The reference's per-point brentq root becomes an in-kernel
+ * safeguarded Newton iteration (converged to 4e-16 relative; brentq stops at xtol = 2e-12). */
+int hepmc_rambo_diet_map(int nparticles, double e_cm, int64_t n, int64_t first_index, uint64_t seed, uint32_t stream_id,
+                         const double* xs_replay_dev, double* out_dev, void* stream);
+/* inverse: p_dev (n, 4*nparticles) -> xs_out_dev (n, 3*nparticles-4) */
+int hepmc_rambo_diet_inverse(int nparticles, double e_cm, int64_t n, const double* p_dev, double* xs_out_dev, void* stream);
+/* flags[i] = (u_i * bound * q_i <= f_i) with u_i the native uniform of item first_index + i;
+ * q_dev may be NULL (then q_scalar is used). */
+int hepmc_accept_flags(const double* f_dev, const double* q_dev, double q_scalar, double bound, int64_t n,
+                       int64_t first_index, uint64_t seed, uint32_t stream_id, unsigned char* flags_dev, void* stream);
+
 /* ---- random-walk Metropolis ensembles: replaces MarkovUpdate.sample (base.py:44-97)
  * + MetropolisUpdate.next_state/accept (metropolis.py:37-50,76-95) + DefaultMetropolis.
  * proposal (:122-124) + proposals.Gaussian.proposal (gaussian.py:25-27), one chain per

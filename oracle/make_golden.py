@@ -594,6 +594,28 @@ def gen_mixing(h):
     save("mixing", **out)
 
 
+def gen_rambo_diet(h):
+    """RamboOnDiet.map / map_inverse (rambo.py:72-151) and MappedDensity (mapping.py)."""
+    out = {}
+    rng = np.random.default_rng(SEED)
+    for n, e_cm in ((3, 50.), (4, 100.), (6, 1000.)):
+        m = h.phase_space.RamboOnDiet(e_cm, n)
+        xs = rng.random((96, 3 * n - 4))
+        p = m.map(xs)
+        out["xs_%d" % n] = xs
+        out["p_%d" % n] = p
+        out["inv_%d" % n] = m.map_inverse(p.copy())
+        out["pdf_%d" % n] = m.pdf(xs)
+    # MappedDensity: a Gaussian in momentum space seen from the unit cube (2 -> 3 particles, 5 dims)
+    m = h.phase_space.RamboOnDiet(50., 3)
+    dens = h.densities.Gaussian(12, mu=10., cov=400.)
+    md = h.phase_space.MappedDensity(dens, m, norm=2.5)
+    xs = points(48, 5, rng)
+    out["mapped_xs"] = xs
+    out["mapped_pdf"] = md.pdf(xs)
+    save("rambo_diet", **out)
+
+
 def gen_importance_ideal(h):
     """tests/test_integration.py:44-52 -- the reference's only exact KAT."""
     np.random.seed(SEED)
@@ -617,6 +639,7 @@ def main():
     gen_importance_ideal(h)
     gen_multichannel(h)
     gen_mixing(h)
+    gen_rambo_diet(h)
     gen_ks_reference()
 
 

@@ -192,6 +192,16 @@ def test_mixing_chains(tag, kind):
     assert_close(chain, g[tag + "_chain"], 1e-10, atol=1e-12)
 
 
+@pytest.mark.parametrize("n,e_cm", [(3, 50.), (4, 100.), (6, 1000.)])
+def test_rambo_diet(n, e_cm):
+    g = G("rambo_diet")
+    p = O.rambo_diet_map(g["xs_%d" % n], e_cm, n)
+    # the reference's root is brentq with xtol = 2e-12: parity to ~1e-11 of e_cm
+    assert_close(p, g["p_%d" % n], 1e-10, atol=1e-11 * e_cm)
+    assert_close(O.rambo_diet_inverse(g["p_%d" % n], e_cm, n), g["inv_%d" % n], 1e-12, atol=1e-13)
+    assert_close(O.rambo_pdf(e_cm, n), g["pdf_%d" % n], 1e-15)
+
+
 def test_philox_kat():
     """Random123 known-answer vectors for Philox4x32-10."""
     kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
