@@ -29,9 +29,9 @@ struct ChainArgs {
 // two standard normals from one Philox call (Box-Muller on two 52-bit uniforms)
 __device__ __forceinline__ void normal_pair(const U4& r, double& z0, double& z1) {
     const double u1 = u52(r.x, r.y), u2 = u52(r.z, r.w);
-    const double rad = sqrt(-2.0 * log(u1));
+    const double rad = sqrt(-2.0 * fm::log(u1));
     double sn, cs;
-    sincospi(2.0 * u2, &sn, &cs);
+    fm::sincos2pi(u2, &sn, &cs);
     z0 = rad * cs;
     z1 = rad * sn;
 }

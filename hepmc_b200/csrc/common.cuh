@@ -7,6 +7,7 @@
 #include <math.h>
 
 #include "../../include/hepmc_b200.h"
+#include "fastmath.cuh"
 
 namespace hepmc {
 

@@ -93,9 +93,9 @@ __global__ void __launch_bounds__(128) mc_sample_kernel(const __grid_constant__ 
                 double z0, z1;
                 if (gauss) {
                     const double u1 = u52(r.x, r.y), u2 = u52(r.z, r.w);
-                    const double rad = sqrt(-2.0 * log(u1));
+                    const double rad = sqrt(-2.0 * fm::log(u1));
                     double sn, cs;
-                    sincospi(2.0 * u2, &sn, &cs);
+                    fm::sincos2pi(u2, &sn, &cs);
                     z0 = rad * cs;
                     z1 = rad * sn;
                     x[2 * k] = row[8 + 2 * k] + row[8 + kChDim + 2 * k] * z0;       // gaussian.py:49-51

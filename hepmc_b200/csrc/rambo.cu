@@ -27,8 +27,8 @@ __device__ __forceinline__ void ld256(const double* p, double& a, double& b, dou
 __device__ __forceinline__ void rambo_q(double u0, double u1, double u2, double u3, double q[4]) {
     const double c = 2.0 * u0 - 1.0;
     double sn, cs;
-    sincospi(2.0 * u1, &sn, &cs);  // phi = 2 pi u1
-    const double q0 = -log(u2 * u3);
+    fm::sincos2pi(u1, &sn, &cs);  // phi = 2 pi u1
+    const double q0 = -fm::log(u2 * u3);
     const double st = q0 * sqrt(1.0 - c * c);
     q[0] = q0;
     q[1] = st * cs;

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) rambo_diet_map_kernel(const __grid_consta
             }
             const double cos_t = 2.0 * x_at(np - 6 + 2 * ip) - 1.0;         // :106
             double sn, cs;
-            sincospi(2.0 * x_at(np - 5 + 2 * ip), &sn, &cs);                // :107
+            fm::sincos2pi(x_at(np - 5 + 2 * ip), &sn, &cs);                // :107
             const double m2 = M_prev * M_prev;
             const double q = 4.0 * M_prev * (1.0 / (8.0 * m2) * sqrt((m2 - M_cur * M_cur) * (m2 - M_cur * M_cur)));  // :108-109,176-177
             const double sin_t = sqrt(1.0 - cos_t * cos_t);
