@@ -85,23 +85,32 @@ class VegasMC(object):
             u_tape, _ = _lib.to_device(replay[1])
             if tuple(idx_tape.shape) != (iterations, ndim, n_total) or idx_tape.shape != u_tape.shape:
                 raise ValueError("replay tapes must have shape (iterations, ndim, sub_eval_count)")
+        grid = self.volumes.device_grid()
+        est_var = torch.zeros((iterations, 2), dtype=torch.float64, device=dev)
+        if fused and ws == 1 and replay is None and not keep_samples and iterations > 0:
+            # whole call in ONE library entry (hepmc_vegas_integrate): all iterations enqueued back
+            # to back, no Python between launches -- matters at small N (launch-latency bound)
+            blk = dens._block()
+            nbytes = int(_lib.load().hepmc_vegas_workspace_bytes(ndim, K, n_total))
+            work = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=dev)
+            _lib.call("hepmc_vegas_integrate", ctypes.byref(blk), _lib.ptr(grid), ndim, K, n_total, int(iterations),
+                      float(self.c), rng.get_seed(), rng.next_stream(iterations), _lib.ptr(est_var), _lib.ptr(work),
+                      nbytes, _lib.stream_ptr())
+            return self._combine(est_var, n_total, iterations, chi, None)
         chunk = _lib.default_chunk(n_total)
         first, n_local, begins = parallel.local_span(n_total, chunk)
         nc_local, n_slots_local = begins[-1], len(begins) - 1
         cols = ndim * K
-        grid = self.volumes.device_grid()
         stats_p = torch.zeros((max(nc_local, 1), 3), dtype=torch.float64, device=dev)
         hist_p = torch.zeros((max(nc_local, 1), cols), dtype=torch.float64, device=dev)
         slot_local = torch.zeros((n_slots_local, 3 + cols), dtype=torch.float64, device=dev)
         slot_stats_l = torch.zeros((n_slots_local, 3), dtype=torch.float64, device=dev)
         slot_hist_l = torch.zeros((n_slots_local, cols), dtype=torch.float64, device=dev)
-        est_var = torch.zeros((iterations, 2), dtype=torch.float64, device=dev)
         begins_c = _lib.i64_array(begins)
         seed = rng.get_seed()
         sid0 = rng.next_stream(iterations)
         blk = dens._block() if fused else engine.none_block(ndim)
         need_pts = keep_samples or not fused
-        sample = VegasSample()
         kept = {"data": [], "function_values": [], "weights": []}
         st = _lib.stream_ptr()
         for j in range(iterations):
@@ -136,9 +145,13 @@ class VegasMC(object):
                 kept["data"].append(x)
                 kept["function_values"].append(f)
                 kept["weights"].append(w)
+        return self._combine(est_var, n_total, iterations, chi, kept if keep_samples else None)
+
+    def _combine(self, est_var, n_total, iterations, chi, kept):
+        """Combination of the iterations, vegas.py:124-142 (host scalars)."""
+        sample = VegasSample()
         ev = est_var.cpu().numpy()            # the only synchronisation of the call
         est_j, var_j = ev[:, 0], ev[:, 1]
-        # combination of the iterations, vegas.py:124-142 (host scalars)
         n = float(n_total)
         if self.var_weighted:
             norm = np.sum(n / var_j)
@@ -152,7 +165,7 @@ class VegasMC(object):
         sample.estimates, sample.variances = est_j, var_j
         if chi:
             sample.chi2 = float(np.sum((est_j - total_est) ** 2 / var_j) / (iterations - 1))
-        if keep_samples and iterations:
+        if kept is not None and iterations:
             sample.data = config.deliver(torch.cat(kept["data"], dim=0))
             sample.function_values = config.deliver(torch.cat(kept["function_values"], dim=0))
             sample.weights = config.deliver(torch.cat(kept["weights"], dim=0))
