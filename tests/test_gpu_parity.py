@@ -695,6 +695,88 @@ def test_hmc_tensor_core_surrogate_is_an_exact_sampler():
     assert acc["tc"] > 0.05
 
 
+# ------------------------------------------------------------------ edge cases: empty, ragged, maximum sizes
+def test_edge_cases_empty_and_ragged():
+    # empty inputs
+    assert H.densities.Camel(3).pdf(np.zeros((0, 3))).shape == (0,)
+    assert H.densities.Camel(3).pot_gradient(np.zeros((0, 3))).shape == (0, 3)
+    assert H.phase_space.Rambo(100., 4).map(np.zeros((0, 16))).shape == (0, 16)
+    assert H.phase_space.Rambo(100., 4).generate(0).shape == (0, 16)
+    g = H.GridVolumes(ndim=2, divisions=4)
+    assert g.pdf(np.zeros((0, 2))).shape == (0,) and g.rvs(0).shape == (0, 2)
+    # one point, one chain, one step
+    s = H.PlainMC(2)(H.densities.Camel(2), 1)
+    assert s.data.shape == (1, 2) and s.integral_err == 0.0
+    met = H.DefaultMetropolis(2, H.densities.Banana(2), H.proposals.Gaussian(2, cov=10 * np.eye(2)))
+    s = met.sample(1, [0., 10.])
+    assert s.data.shape == (1, 2) and s.accepted == 0
+    # ragged sizes around the chunk / tile boundaries, native draws against the oracle
+    for n in (1, 31, 255, 257, 2047, 2049, 4097):
+        H.seed(50 + n)
+        s = H.PlainMC(3)(H.densities.Camel(3), n)
+        u = O.philox_uniforms(50 + n, 0, np.arange(n), 3)
+        integral, err, f = O.plain_mc(O.camel_pdf, u)
+        assert np.array_equal(s.data, u)
+        assert_close(s.integral, integral, RTOL)
+        assert_close(s.integral_err, err, 1e-10, atol=1e-300)
+    for n in (1, 33, 2049):
+        H.seed(70 + n)
+        mc = H.VegasMC(3, divisions=7)
+        s = mc(H.densities.Camel(3), n, 2)
+        tapes = [O.philox_vegas_draws(70 + n, j, np.arange(n), 3, 7) for j in range(2)]
+        r = O.vegas(O.camel_pdf, 3, 7, np.stack([t[0] for t in tapes]), np.stack([t[1] for t in tapes]))
+        assert_close(s.estimates, r["est_j"], RTOL)
+        if n > 1:
+            assert_close(np.stack(mc.volumes.bounds), r["bounds_history"][-1], RTOL, atol=1e-15)
+
+
+def test_edge_cases_maximum_sizes():
+    rs = np.random.default_rng(9)
+    # ndim = 32 (HEPMC_MAX_DIM): densities and the runtime-ndim VEGAS / plain kernels
+    xs = rs.random((257, 32))
+    assert_close(H.densities.Camel(32).pdf(xs), O.camel_pdf(xs), RTOL, atol=1e-300)
+    assert_close(H.densities.Gaussian(32, mu=0.5, cov=0.3).pot_gradient(xs), O.gaussian_pot_gradient(xs, 0.5, 0.3), RTOL, atol=1e-15)
+    with pytest.raises(RuntimeError):
+        H.densities.Camel(33).pdf(rs.random((2, 33)))
+    H.seed(5)
+    n, ndim, K = 3000, 32, 5
+    mc = H.VegasMC(ndim, divisions=K)
+    dens = H.densities.Gaussian(ndim, mu=0.5, cov=0.05)
+    s = mc(dens, n, 2, keep_samples=False)
+    tapes = [O.philox_vegas_draws(5, j, np.arange(n), ndim, K) for j in range(2)]
+    r = O.vegas(lambda x: O.gaussian_pdf(x, 0.5, 0.05), ndim, K, np.stack([t[0] for t in tapes]), np.stack([t[1] for t in tapes]))
+    assert_close(s.estimates, r["est_j"], RTOL)
+    assert_close(np.stack(mc.volumes.bounds), r["bounds_history"][-1], RTOL, atol=1e-15)
+    # divisions = 255 (HEPMC_MAX_DIVISIONS: bin ids are bytes), ndim = 2
+    H.seed(6)
+    mc = H.VegasMC(2, divisions=255)
+    s = mc(H.densities.Camel(2), 20000, 2, keep_samples=False)
+    tapes = [O.philox_vegas_draws(6, j, np.arange(20000), 2, 255) for j in range(2)]
+    r = O.vegas(O.camel_pdf, 2, 255, np.stack([t[0] for t in tapes]), np.stack([t[1] for t in tapes]))
+    assert_close(s.estimates, r["est_j"], RTOL)
+    assert_close(np.stack(mc.volumes.bounds), r["bounds_history"][-1], 1e-11, atol=1e-15)
+    with pytest.raises(RuntimeError):
+        H.VegasMC(2, divisions=256)(H.densities.Camel(2), 100, 1)
+    # chains at ndim = 16 (HEPMC_MAX_CHAIN_DIM)
+    H.seed(7)
+    C, T, nd = 33, 40, 16
+    x0 = 0.5 + 0.01 * rs.standard_normal((C, nd))
+    met = H.DefaultMetropolis(nd, H.densities.Gaussian(nd, mu=0.5, cov=0.01), H.proposals.Gaussian(nd, cov=0.0004 * np.eye(nd)))
+    s = met.sample(T, x0)
+    w = O.philox_words(7, 0, np.arange(C), 9 * (T - 1))
+    z = np.empty((C, T - 1, nd)); u = np.empty((C, T - 1))
+    for t in range(T - 1):
+        for k in range(8):
+            z0, z1 = O.box_muller(O.u52(w[:, 9 * t + k, 0], w[:, 9 * t + k, 1]), O.u52(w[:, 9 * t + k, 2], w[:, 9 * t + k, 3]))
+            z[:, t, 2 * k], z[:, t, 2 * k + 1] = z0, z1
+        u[:, t] = O.u52(w[:, 9 * t + 8, 0], w[:, 9 * t + 8, 1])
+    chain, acc = O.metropolis_chains(lambda x: O.gaussian_pdf(x, 0.5, 0.01), x0, z, u, np.full(nd, 0.02))
+    assert np.array_equal(s.accepted, acc)
+    assert_close(s.data, chain, 1e-10, atol=1e-12)
+    with pytest.raises(RuntimeError):
+        H.DefaultMetropolis(17, H.densities.Gaussian(17), H.proposals.Gaussian(17)).sample(5, np.zeros(17))
+
+
 def test_fp64_probe_and_device_info():
     info = _lib.device_info()
     assert info["cc"][0] == 10 and info["sm_count"] >= 100
