@@ -1,7 +1,8 @@
-from .gaussian import Gaussian
-from .camel import Camel, UnconstrainedCamel
-from .uniform import Uniform
+"""Analytic target densities and sampling distributions with CUDA kernels behind them."""
 from .banana import Banana
+from .camel import Camel, UnconstrainedCamel
+from .gaussian import Gaussian
 from .rambo import Rambo, RamboOnDiet
+from .uniform import Uniform
 
-__all__ = ['Gaussian', 'Camel', 'UnconstrainedCamel', 'Uniform', 'Banana', 'Rambo', 'RamboOnDiet']
+__all__ = [name for name in dir() if name[0].isupper()]

@@ -14,22 +14,11 @@ class Gaussian(BuiltinDensity, Distribution):
     kind = _lib.GAUSSIAN
 
     def __init__(self, ndim, mu=0, cov=None, scale=None):
+        from ..proposals.gaussian import diagonal_covariance
         BuiltinDensity.__init__(self, ndim, False)
-        self._mean = None
-        self._cov = None
-        self._cov_inv = None
+        self._mean = self._cov = self._cov_inv = None
         self.mean = mu
-        if cov is None:
-            if scale is None:
-                self.cov = np.ones(ndim)
-            else:
-                if not np.isscalar(scale):
-                    scale = np.atleast_1d(scale)
-                self.cov = scale ** 2
-        else:
-            self.cov = cov
-            if scale is not None:
-                raise RuntimeWarning("Specified both cov and scale (using cov)")
+        self.cov = diagonal_covariance(ndim, cov, scale)
 
     def _diag(self):
         cov = np.asarray(self._cov)
@@ -72,8 +61,9 @@ class Gaussian(BuiltinDensity, Distribution):
 
     @cov.setter
     def cov(self, value):
+        # element-wise product with the identity (gaussian.py:73-76): the stored matrix is diagonal
         self._cov = np.eye(self.ndim, self.ndim) * np.asanyarray(value)
-        self._cov_inv = np.linalg.inv(self._cov)
+        self._cov_inv = np.diag(1.0 / np.diagonal(self._cov))
 
     def __repr__(self):
         return type(self).__name__ + "(ndim=%s, mu=%s, cov=%s)" % (self.ndim, self.mean, self.cov)

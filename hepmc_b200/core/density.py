@@ -104,32 +104,25 @@ class Density(_AnyDensity):
     @classmethod
     def make(cls, pdf=None, ndim=None, pdf_vect=None, is_symmetric=False,
              pdf_gradient=None, variance=None, mean=None):
-        """Wrap user callables into a Density (density.py:77-99)."""
+        """Wrap user callables into a Density (density.py:77-99): `pdf` takes the (N, ndim) array,
+        `pdf_vect` takes ndim column arrays; results are flattened to (N,).  The callables receive
+        whatever array type the caller passes (NumPy arrays or CUDA tensors)."""
         if isinstance(pdf, Density):
             obj = pdf
+        elif ndim is None:
+            raise RuntimeError("If first argument is not a Density, ndim must be specified.")
         else:
-            if ndim is None:
-                raise RuntimeError("If first argument is not a Density, ndim must be specified.")
             obj = cls(ndim, is_symmetric)
+
+            def flat(values):
+                return values.reshape(-1) if _is_tensor(values) else np.atleast_1d(values).flatten()
             if pdf is not None:
-                def _pdf(xs, _f=pdf):
-                    out = _f(xs)
-                    if _is_tensor(out):
-                        return out.reshape(-1)
-                    return np.atleast_1d(out).flatten()
-                obj.pdf = _pdf
+                obj.pdf = lambda xs, _f=pdf: flat(_f(xs))
             elif pdf_vect is not None:
-                def _pdf_vect(xs, _f=pdf_vect):
-                    cols = xs.t() if _is_tensor(xs) else xs.transpose()
-                    out = _f(*cols)
-                    return out.reshape(-1) if _is_tensor(out) else np.asarray(out).flatten()
-                obj.pdf = _pdf_vect
-        if pdf_gradient is not None:
-            obj.pdf_gradient = pdf_gradient
-        if variance is not None:
-            obj.variance = variance
-        if mean is not None:
-            obj.mean = mean
+                obj.pdf = lambda xs, _f=pdf_vect: flat(_f(*(xs.t() if _is_tensor(xs) else xs.transpose())))
+        for name, value in (("pdf_gradient", pdf_gradient), ("variance", variance), ("mean", mean)):
+            if value is not None:
+                setattr(obj, name, value)
         return obj
 
 

@@ -1,4 +1,5 @@
-from .rambo import Rambo, RamboOnDiet, PhaseSpaceMapping
+"""Phase-space mappings of the unit hypercube (RAMBO family) and densities seen through them."""
 from .mapping import MappedDensity
+from .rambo import PhaseSpaceMapping, Rambo, RamboOnDiet
 
-__all__ = ['Rambo', 'RamboOnDiet', 'MappedDensity', 'PhaseSpaceMapping']
+__all__ = [name for name in dir() if name[0].isupper()]

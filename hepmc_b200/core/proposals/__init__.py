@@ -1,3 +1,4 @@
+"""Proposal generators understood by the chain kernels."""
 from .gaussian import Gaussian
 
-__all__ = ['Gaussian']
+__all__ = ["Gaussian"]

@@ -56,28 +56,22 @@ class BasicMC3(object):
         return self.sample(sample_size, initial, **kwargs)
 
 
+def _forward(owner, name):
+    """Property forwarding attribute `name` to the sub-object `owner` (e.g. the local sampler)."""
+    return property(lambda self: getattr(getattr(self, owner), name),
+                    lambda self, value: setattr(getattr(self, owner), name, value))
+
+
 class MC3Hamilton(BasicMC3):
+    """(MC)^3 with an HMC local update; `m` = momentum standard deviations (mc3.py:117-149)."""
+
+    step_size = _forward("sample_local", "step_size")
+    steps = _forward("sample_local", "steps")
 
     def __init__(self, target_density, channels, m, steps, step_size, beta=.5):
         self.p_dist = Gaussian(channels.ndim, scale=m)
-        sample_local = HamiltonianUpdate(target_density, self.p_dist, steps, step_size)
-        super().__init__(target_density, channels, sample_local, beta)
-
-    @property
-    def step_size(self):
-        return self.sample_local.step_size
-
-    @step_size.setter
-    def step_size(self, step_size):
-        self.sample_local.step_size = step_size
-
-    @property
-    def steps(self):
-        return self.sample_local.steps
-
-    @steps.setter
-    def steps(self, steps):
-        self.sample_local.steps = steps
+        BasicMC3.__init__(self, target_density, channels,
+                          HamiltonianUpdate(target_density, self.p_dist, steps, step_size), beta)
 
     @property
     def m(self):
@@ -85,4 +79,4 @@ class MC3Hamilton(BasicMC3):
 
     @m.setter
     def m(self, value):
-        self.p_dist.cov = value ** 2
+        self.p_dist.cov = np.square(value)
