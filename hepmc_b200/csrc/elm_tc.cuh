@@ -169,7 +169,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// development knob (scripts only): 1 = skip GEMM-2, 2 = skip exp, 4 = GEMM-2 with 1 MMA per tile
+// development knob (scripts only): 1 = skip GEMM-2, 2 = skip exp, 4 = GEMM-2 with 2 MMAs per tile,
+// 8 = GEMM-1 with 1 MMA per tile, 16 = exp stage without TMEM access
 __device__ int g_tc_debug = 0;
 
 struct Shared {
@@ -259,6 +260,7 @@ __device__ __forceinline__ void issue_g1(uint32_t tmem_base, uint32_t b1_saddr, 
     const uint32_t a = tmem_base + COL_A1;
     constexpr uint32_t STEP = (2 * TILE_N * 16) >> 4;   // two 16-byte K chunks per MMA, in descriptor units
     umma_tf32_ts_lh<0>(d, a, lo, hi, idesc);
+    if (g_tc_debug & 8) return;
 #pragma unroll
     for (int ks = 1; ks < K1 / 8; ++ks) umma_tf32_ts_lh<1>(d, a + ks * 8, lo + ks * STEP, hi, idesc);
 }
@@ -269,7 +271,7 @@ __device__ __forceinline__ void issue_g2(uint32_t tmem_base, uint32_t b2_saddr, 
     const uint64_t bd0 = make_desc(b2_saddr + t * B2_TILE_BYTES, N2 * 16, 128);
     const uint32_t lo = (uint32_t)bd0, hi = (uint32_t)(bd0 >> 32);
     constexpr uint32_t STEP = (2 * N2 * 16) >> 4;
-    const int nk = n_cols >> 3;
+    const int nk = (g_tc_debug & 4) ? 2 : (n_cols >> 3);
 #pragma unroll
     for (int ks = 0; ks < TILE_N / 8; ++ks) {
         if (ks < nk) {
