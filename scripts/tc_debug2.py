@@ -7,7 +7,7 @@ H.set_outputs("torch")
 lib = _lib.load()
 rs = np.random.default_rng(0)
 x0h = torch.full((148 * 128, 8), 1 / 3, device="cuda", dtype=torch.float64)
-for mode in (0, 2, 6, 10, 14, 3):
+for mode in (0, 2):
     for nodes in (128, 256, 512, 1024):
         basis = H.surrogate.GaussianBasis(8)
         params = (rs.random((nodes, 8)), 0.01 + 0.99 * rs.random(nodes), None)
