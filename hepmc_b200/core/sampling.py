@@ -1,9 +1,8 @@
 """Result containers (mirror of hepmc/core/sampling.py:23-145, host-side and thin).
 
-`data`, `weights`, `function_values` may be NumPy arrays or CUDA tensors; the lazy
-summaries are computed with whichever library holds the data.  The O(N^2)
-autocovariance-based statistics of the reference (effective sample size, bin-wise chi^2)
-are post-hoc host analysis and are not part of the accelerated path.
+`data`, `weights`, `function_values` may be NumPy arrays or CUDA tensors; mean / variance
+are computed with whichever library holds the data.  The effective sample size and the
+bin-wise chi^2 (sampling.py:79-94) run on the device through core/util/stat_tools.py.
 """
 import json
 import os
@@ -30,10 +29,14 @@ class Sample(object):
         self.weights = None
         self._variance = None
         self._mean = None
+        self._bin_wise_chi2 = None
+        self._effective_sample_size = None
         self._sample_info = [
             ('size', 'data (size)', '%s'),
             ('mean', 'mean', '%s'),
             ('variance', 'variance', '%s'),
+            ('bin_wise_chi2', 'bin-wise chi^2', '%.4g, p=%.4g, N=%d'),
+            ('effective_sample_size', 'effective sample size', '%s'),
         ]
         for key in kwargs:
             setattr(self, key, kwargs[key])
@@ -72,11 +75,22 @@ class Sample(object):
 
     @property
     def effective_sample_size(self):
-        return None
+        """Needs the target's known `mean` and `variance` (sampling.py:79-88); None otherwise."""
+        if self._effective_sample_size is None and _set(self.data, self.target):
+            try:
+                moments = self.target.mean, self.target.variance
+            except AttributeError:
+                return None
+            from .util import stat_tools
+            self._effective_sample_size = stat_tools.effective_sample_size(self, *moments)
+        return self._effective_sample_size
 
     @property
     def bin_wise_chi2(self):
-        return None
+        if self._bin_wise_chi2 is None and _set(self.data, self.target):
+            from .util import stat_tools
+            self._bin_wise_chi2 = stat_tools.bin_wise_chi2(self)
+        return self._bin_wise_chi2
 
     def save(self, file_path=None):
         if file_path is None:

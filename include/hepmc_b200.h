@@ -304,6 +304,41 @@ int hepmc_mc3_chains(const hepmc_density_t* dens, const double* channel_table_de
 int hepmc_elm_eval(const hepmc_elm_t* elm, int ndim, int what, int precision,
                    const double* xs_dev, int64_t n, double* out_dev, void* stream);
 
+/* ---- sample statistics: replaces auto_cov / auto_corr / effective_sample_size / bin_wise_chi2
+ * (core/util/stat_tools.py:11-129), the reductions Sample.__repr__ shows
+ * (core/sampling.py:79-94).  data_dev is (n_chains, n_steps, ndim) row-major; mean_dev and
+ * var_dev are (ndim,) -- the KNOWN target moments, as in the reference. -------------------- */
+/* out_dev (n_chains, n_lags, ndim): lag-k autocovariance sum_t (x_t-mean)(x_{t+k}-mean) / n_steps
+ * for k in [lag_begin, lag_begin + n_lags); lag 0 is var (stat_tools.py:17-37). */
+int hepmc_autocov(const double* data_dev, int64_t n_chains, int64_t n_steps, int ndim,
+                  const double* mean_dev, const double* var_dev, int64_t lag_begin, int64_t n_lags,
+                  double* out_dev, void* stream);
+/* ess_dev (n_chains, ndim) = n / (1 + 2 sum_lag (1 - lag/n) rho_lag), rho_lag the unbiased
+ * autocorrelation, summed from lag 1 while rho >= 0.05 and lag < n - 1 (stat_tools.py:46-70).
+ * lag_dev (n_chains, ndim) or NULL receives the lag at which each sum stopped.  n_steps >= 2. */
+int hepmc_effective_sample_size(const double* data_dev, int64_t n_chains, int64_t n_steps, int ndim,
+                                const double* mean_dev, const double* var_dev,
+                                double* ess_dev, int64_t* lag_dev, void* stream);
+/* np.histogramdd as bin_wise_chi2 calls it (stat_tools.py:108): edges_dev holds the ndim edge
+ * arrays back to back (nbins_host[d] + 1 doubles each, increasing); counts_dev has
+ * prod(nbins) entries in C order and is zeroed here.  A point on the last edge belongs to
+ * the last bin; points outside (or NaN) are dropped. */
+int hepmc_histogramdd(const double* data_dev, int64_t n, int ndim, const double* edges_dev,
+                      const int* nbins_host, unsigned long long* counts_dev, void* stream);
+/* int_steps uniform points inside each of the m bins flat_dev[j] (C-order flat indices):
+ * out_dev (m * int_steps, ndim), x = low + (high - low) u (stat_tools.py:122-123).
+ * u_replay_dev (m, int_steps, ndim) or NULL (native generator). */
+int hepmc_bin_points(int ndim, const double* edges_dev, const int* nbins_host,
+                     const int64_t* flat_dev, int64_t m, int int_steps,
+                     uint64_t seed, uint32_t stream_id, const double* u_replay_dev,
+                     double* out_dev, void* stream);
+/* expected_dev[j] = mean_s pdf_dev[j, s] * sample_size * bin_volume; out_dev[0] =
+ * sum over bins with expected >= min_count of (count - expected)^2 / expected (what
+ * scipy.stats.chisquare returns, stat_tools.py:125-127), out_dev[1] = number of such bins. */
+int hepmc_bin_chi2(const double* pdf_dev, const int64_t* flat_dev, const unsigned long long* counts_dev,
+                   int64_t m, int int_steps, double sample_size, double bin_volume, double min_count,
+                   double* expected_dev, double* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

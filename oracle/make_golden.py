@@ -616,6 +616,65 @@ def gen_rambo_diet(h):
     save("rambo_diet", **out)
 
 
+def gen_stats(h):
+    """stat_tools.effective_sample_size / auto_cov / fd_bins / bin_wise_chi2 (:11-129) on
+    reference Metropolis chains over Camel(2) and a 3-D Gaussian.
+
+    Two accommodations for the authoring container, neither touching the arithmetic:
+    np.random.uniform is wrapped to log the uniforms behind it (legacy uniform ==
+    low + (high - low) * random_sample, asserted), and scipy.stats.chisquare is called with
+    sum_check=False -- SciPy >= 1.16 otherwise rejects f_obs/f_exp whose sums differ, which
+    the SciPy the reference was written for (>= 1.0) did not."""
+    from scipy import stats as sps
+    import importlib
+    st = importlib.import_module("hepmc.core.util.stat_tools")
+    out = {}
+    # legacy uniform identity
+    np.random.seed(3)
+    a = np.random.uniform([0., 1.], [2., 5.], (7, 2))
+    np.random.seed(3)
+    b = np.array([0., 1.]) + (np.array([2., 5.]) - np.array([0., 1.])) * np.random.random_sample((7, 2))
+    assert np.array_equal(a, b), "legacy uniform mismatch"
+
+    orig_uniform, orig_chisq = np.random.uniform, sps.chisquare
+    cases = (
+        ("camel", h.densities.Camel(2), h.proposals.Gaussian(2, cov=np.diag([0.004, 0.004])), [0.35, 0.3], 6000),
+        ("gauss", h.densities.Gaussian(3, mu=0.25, cov=0.7), h.proposals.Gaussian(3, cov=0.5 * np.eye(3)),
+         [0.1, -0.2, 0.3], 4000),
+    )
+    for name, target, prop, x0, T in cases:
+        np.random.seed(SEED)
+        sample = h.DefaultMetropolis(target.ndim, target, prop).sample(T, x0, log_every=-1)
+        sample.target = target
+        out[name + "_data"] = np.array(sample.data)
+        out[name + "_mean"] = np.asarray(target.mean, dtype=np.float64) * np.ones(target.ndim)
+        out[name + "_var"] = np.asarray(target.variance, dtype=np.float64) * np.ones(target.ndim)
+        out[name + "_ess"] = st.effective_sample_size(sample, target.mean, target.variance)
+        short = sample.data[:300]
+        out[name + "_acov300"] = st.auto_cov(short, np.mean(short, 0), np.var(short, 0))
+        out[name + "_fd_bins"] = st.fd_bins(sample)
+        tape = []
+
+        def uniform(low, high, size):
+            u = np.random.random_sample(size)
+            tape.append(u.copy())
+            return np.asarray(low) + (np.asarray(high) - np.asarray(low)) * u
+        np.random.uniform = uniform
+        sps.chisquare = lambda f_obs, f_exp: orig_chisq(f_obs, f_exp=f_exp, sum_check=False)
+        st.stats.chisquare = sps.chisquare
+        try:
+            for tag, kw in (("auto", {}), ("fixed", dict(bins=12, min_count=5, int_steps=64))):
+                del tape[:]
+                res = st.bin_wise_chi2(sample, **kw)
+                out["%s_chi2_%s" % (name, tag)] = np.array(res, dtype=np.float64)
+                out["%s_chi2_%s_u" % (name, tag)] = np.stack(tape)
+        finally:
+            np.random.uniform = orig_uniform
+            sps.chisquare = orig_chisq
+            st.stats.chisquare = orig_chisq
+    save("stats", **out)
+
+
 def gen_importance_ideal(h):
     """tests/test_integration.py:44-52 -- the reference's only exact KAT."""
     np.random.seed(SEED)
@@ -640,6 +699,7 @@ def main():
     gen_multichannel(h)
     gen_mixing(h)
     gen_rambo_diet(h)
+    gen_stats(h)
     gen_ks_reference()
 
 

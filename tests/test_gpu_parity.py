@@ -781,3 +781,89 @@ def test_fp64_probe_and_device_info():
     info = _lib.device_info()
     assert info["cc"][0] == 10 and info["sm_count"] >= 100
     assert _lib.fp64_probe(1 << 12) > 1e12
+
+
+# ------------------------------------------------------------------ sample statistics (stat_tools)
+def _stats_targets():
+    return (("camel", H.densities.Camel(2)), ("gauss", H.densities.Gaussian(3, mu=0.25, cov=0.7)))
+
+
+def test_effective_sample_size_vs_reference():
+    """stat_tools.effective_sample_size / auto_cov on the reference's own chains (fixed-order
+    device sums vs NumPy einsum: 1e-11 relative)."""
+    from hepmc_b200.core.util import stat_tools
+    g = G("stats")
+    for name, target in _stats_targets():
+        data = g[name + "_data"]
+        smp = H.core.sampling.Sample(data=data, target=target)
+        ess, lags = stat_tools.effective_sample_size(smp, target.mean, target.variance, return_lags=True)
+        assert_close(ess, g[name + "_ess"], 1e-11)
+        assert np.array_equal(lags, O.effective_sample_size(data, g[name + "_mean"], g[name + "_var"])[1])
+        assert_close(smp.effective_sample_size, g[name + "_ess"], 1e-11)     # the Sample property
+        short = data[:300]
+        acov = stat_tools.auto_cov(short)
+        assert acov.shape == (300, data.shape[1])
+        assert_close(acov, g[name + "_acov300"], 1e-11, atol=1e-17)
+        assert_close(stat_tools.auto_corr(short)[0], np.ones(data.shape[1]), 0)
+        assert_close(stat_tools.lag_auto_cov(short, 7), g[name + "_acov300"][7], 1e-11, atol=1e-17)
+        assert_close(stat_tools.auto_cov(short, max_lag=11), g[name + "_acov300"][:11], 1e-11, atol=1e-17)
+    # ensemble form: chains stacked -> per-chain answers identical to the single-chain calls
+    a, b = g["camel_data"][:3000], g["camel_data"][3000:]
+    tgt = H.densities.Camel(2)
+    ens = stat_tools.effective_sample_size(np.stack([a, b]), tgt.mean, tgt.variance)
+    assert np.array_equal(ens[0], stat_tools.effective_sample_size(a, tgt.mean, tgt.variance))
+    assert np.array_equal(ens[1], stat_tools.effective_sample_size(b, tgt.mean, tgt.variance))
+    # shortest legal chain, and the loud failure below it
+    assert stat_tools.effective_sample_size(np.array([[0.1], [0.9]]), 0.5, 0.1).shape == (1,)
+    with pytest.raises(RuntimeError):
+        stat_tools.effective_sample_size(np.array([[0.1]]), 0.5, 0.1)
+
+
+def test_histogramdd_bit_exact():
+    from hepmc_b200.core.util import stat_tools
+    g = G("stats")
+    rs = np.random.RandomState(5)
+    for data, bins, rng_ in ((g["camel_data"], (11, 12), None), (g["gauss_data"], 7, None),
+                             (g["gauss_data"], (5, 6, 7), ((-1, 1), (-0.5, 2), (0, 0.3))),
+                             (rs.rand(5000, 1), 50, None), (np.full((10, 2), 0.25), 4, None),
+                             (rs.randn(3000, 2), (np.array([-1., 0., 0.5, 3.]), 5), None)):
+        cnt, edges = stat_tools.histogramdd(data, bins, rng_)
+        ref, ref_edges = np.histogramdd(data, bins, rng_)
+        assert np.array_equal(cnt.cpu().numpy(), ref.astype(np.int64))
+        for e, r in zip(edges, ref_edges):
+            assert np.array_equal(e, r)
+    d = g["gauss_data"].copy()
+    d[5, 1] = np.nan
+    cnt, _ = stat_tools.histogramdd(d, 6, ((-3, 3),) * 3)
+    assert int(cnt.sum()) == int(np.histogramdd(np.delete(d, 5, axis=0), 6, ((-3, 3),) * 3)[0].sum())
+
+
+def test_bin_wise_chi2_vs_reference():
+    """stat_tools.bin_wise_chi2 with the reference's uniforms replayed, then with the native
+    generator (statistically equivalent: the per-bin integrals use other points)."""
+    from hepmc_b200.core.util import stat_tools
+    g = G("stats")
+    for name, target in _stats_targets():
+        data = g[name + "_data"]
+        smp = H.core.sampling.Sample(data=data, target=target)
+        assert np.array_equal(stat_tools.fd_bins(smp), g[name + "_fd_bins"])
+        for tag, kw in (("auto", {}), ("fixed", dict(bins=12, min_count=5, int_steps=64))):
+            ref = g["%s_chi2_%s" % (name, tag)]
+            red, p, n = stat_tools.bin_wise_chi2(smp, replay=g["%s_chi2_%s_u" % (name, tag)], **kw)
+            assert n == int(ref[2])
+            assert_close(red, ref[0], 1e-11)
+            assert_close(p, ref[1], 1e-8)
+        H.seed(3)
+        red, p, n = smp.bin_wise_chi2
+        ref = g[name + "_chi2_auto"]
+        assert abs(n - int(ref[2])) <= 3 and abs(red / ref[0] - 1) < 0.25
+        assert "bin-wise chi^2: %.4g" % red in repr(smp)
+    # a sample that follows its target: chi^2/dof ~ 1
+    H.seed(21)
+    tgt = H.densities.Gaussian(2, mu=0.0, cov=1.0)
+    smp = H.core.sampling.Sample(data=tgt.rvs(200000), target=tgt)
+    red, p, n = smp.bin_wise_chi2
+    assert n > 100 and abs(red - 1) < 5 * math.sqrt(2.0 / (n - 1)) + 0.05
+    # nothing qualifies -> (None, None, None) like the reference
+    assert stat_tools.bin_wise_chi2(H.core.sampling.Sample(data=g["camel_data"][:50], target=H.densities.Camel(2)),
+                                    bins=40) == (None, None, None)

@@ -237,3 +237,34 @@ def test_ks_restatement():
     from oracle.stats_oracle import ks
     for fam in ("cv", "hmc"):
         assert_close(np.array(ks(g["chain_hist_" + fam], g["truth"])), g["chain_ks_" + fam], 1e-13)
+
+
+def _stats_cases():
+    return (("camel", lambda xs: O.camel_pdf(xs)),
+            ("gauss", lambda xs: O.gaussian_pdf(xs, np.full(3, 0.25), np.full(3, 0.7))))
+
+
+def test_effective_sample_size_restatement():
+    """stat_tools.py:17-70 on reference Metropolis chains."""
+    g = G("stats")
+    for name, _ in _stats_cases():
+        data = g[name + "_data"]
+        ess, stop = O.effective_sample_size(data, g[name + "_mean"], g[name + "_var"])
+        assert_close(ess, g[name + "_ess"], 1e-12)
+        assert np.all(stop >= 1)
+        short = data[:300]
+        assert_close(O.auto_cov(short, np.mean(short, 0), np.var(short, 0)), g[name + "_acov300"], 1e-13, atol=1e-18)
+
+
+def test_bin_wise_chi2_restatement():
+    """stat_tools.py:73-129 with the reference's uniforms replayed."""
+    g = G("stats")
+    for name, pdf in _stats_cases():
+        data = g[name + "_data"]
+        assert np.array_equal(O.fd_bins(data), g[name + "_fd_bins"])
+        for tag, kw in (("auto", {}), ("fixed", dict(bins=12, min_count=5, int_steps=64))):
+            red, p, n, _ = O.bin_wise_chi2(data, pdf, u_tape=g["%s_chi2_%s_u" % (name, tag)], **kw)
+            ref = g["%s_chi2_%s" % (name, tag)]
+            assert n == int(ref[2])
+            assert_close(red, ref[0], 1e-12)
+            assert_close(p, ref[1], 1e-9)
