@@ -145,6 +145,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     H.set_outputs("torch")
     dev = torch.device("cuda", local_rank)
@@ -213,10 +215,10 @@ def run_b200(args):
     achieved = FLOP_PER_POINT * n_local / (kernel_ms * 1e-3) / 1e12
 
     others = {}
-    # the other configs are single-GPU workloads: only in the N = 1 run (under torch.distributed the
-    # library would look for its peers in every reduction)
-    if world == 1 and not args.no_others:
-        others = other_workloads(H, _lib, torch, fp64_peak, world == 1 and not args.no_cpu)
+    # the other configs: EVERY rank runs them (the library's reductions look for their peers); the
+    # collective-free ones (RAMBO, RWM, HMC) are index-range sharded, whole-job size fixed
+    if not args.no_others:
+        others = other_workloads(H, _lib, torch, fp64_peak, world == 1 and not args.no_cpu, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -307,56 +309,71 @@ def cpu_ports():
     return out
 
 
-def other_workloads(H, _lib, torch, fp64_peak, with_cpu):
-    """The other configs BASELINE.json names, single GPU, device-timed."""
+def other_workloads(H, _lib, torch, fp64_peak, with_cpu, rank=0, world=1):
+    """The other configs BASELINE.json names, device-timed.  Called by every rank: the
+    independent-item workloads are split by global index range (parallel.item_span), timed
+    between barriers, max over ranks; values are whole-job throughputs."""
+    import torch.distributed as dist
+    from hepmc_b200 import parallel
     out = {}
 
     def timed(fn, reps=3):
         fn()
-        torch.cuda.synchronize()
         ts = []
         for _ in range(reps):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
             b.record()
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b) * 1e-3)
-        return float(np.mean(ts))
+        t = torch.tensor([float(np.mean(ts))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
     hbm = None
     try:
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         hbm = 6650.0
     cpu = cpu_ports() if with_cpu else {}
-    # C1: 2-D camel, 1M points: plain MC and VEGAS 10 x 1e5 (launch-latency dominated at this size)
-    camel2 = H.densities.Camel(2)
-    t = timed(lambda: H.PlainMC(2)(camel2, 1_000_000, keep_samples=False))
-    out["c1_plain2"] = {"metric": "camel-2D plain MC points/s (1e6 points, whole call)", "value": 1e6 / t,
-                        "cpu_baseline": cpu.get("plain2")}
-    mc2 = H.VegasMC(2, divisions=50)
-    t = timed(lambda: mc2(camel2, 100_000, 10, keep_samples=False))
-    out["c1_vegas2"] = {"metric": "camel-2D VEGAS points/s (10 x 1e5 points, whole call)", "value": 1e6 / t,
-                        "cpu_baseline": cpu.get("vegas2")}
-    # C2: RAMBO 2->4, sqrt(s) = 100 GeV: 2^27 points per launch (16 GiB of output, larger than L2)
+    if world == 1:
+        # C1: 2-D camel, 1M points: plain MC and VEGAS 10 x 1e5 (launch-latency dominated at this
+        # size, so only quoted on one GPU)
+        camel2 = H.densities.Camel(2)
+        t = timed(lambda: H.PlainMC(2)(camel2, 1_000_000, keep_samples=False))
+        out["c1_plain2"] = {"metric": "camel-2D plain MC points/s (1e6 points, whole call)", "value": 1e6 / t,
+                            "cpu_baseline": cpu.get("plain2")}
+        mc2 = H.VegasMC(2, divisions=50)
+        t = timed(lambda: mc2(camel2, 100_000, 10, keep_samples=False))
+        out["c1_vegas2"] = {"metric": "camel-2D VEGAS points/s (10 x 1e5 points, whole call)", "value": 1e6 / t,
+                            "cpu_baseline": cpu.get("vegas2")}
+    # C2: RAMBO 2->4, sqrt(s) = 100 GeV: 2^27 points per launch whole job (16 GiB of output,
+    # larger than L2 at every N)
     m = H.phase_space.Rambo(100., 4)
     nr = 1 << 27
-    buf = torch.empty((nr, 16), dtype=torch.float64, device="cuda")
-    t = timed(lambda: m.generate(nr, out=buf))
+    first, cnt = parallel.item_span(nr, rank, world)
+    buf = torch.empty((cnt, 16), dtype=torch.float64, device="cuda")
+    t = timed(lambda: m.generate(cnt, first_index=first, out=buf))
     del buf
     out["rambo"] = {"metric": "RAMBO 2->4 PS-points/s", "value": nr / t, "points": nr,
-                    "roofline": {"bound": "hbm", "achieved": nr * 128 / t / 1e9, "peak": hbm, "unit": "GB/s",
-                                 "frac": nr * 128 / t / 1e9 / hbm, "bytes_per_point": 128,
-                                 "fp64_tflops_algorithmic": 183 * nr / t / 1e12},
+                    "roofline": {"bound": "hbm", "achieved": nr * 128 / t / 1e9 / world, "peak": hbm, "unit": "GB/s",
+                                 "frac": nr * 128 / t / 1e9 / world / hbm, "bytes_per_point": 128, "per": "GPU",
+                                 "fp64_tflops_algorithmic": 183 * nr / t / 1e12 / world},
                     "cpu_baseline": cpu.get("rambo")}
     # C4: banana 2-D RWM: 1e6 chains x 1e3 steps per launch (the 1e4-step config is 10 such launches)
     C, T = 1_000_000, 1001
+    first, cnt = parallel.item_span(C, rank, world)
     met = H.DefaultMetropolis(2, H.densities.Banana(2), H.proposals.Gaussian(2, cov=10 * np.eye(2)))
-    x0 = torch.tensor([[0., 10.]], device="cuda", dtype=torch.float64).repeat(C, 1)
-    t = timed(lambda: met.sample(T, x0, store_chain=False))
+    x0 = torch.tensor([[0., 10.]], device="cuda", dtype=torch.float64).repeat(cnt, 1)
+    t = timed(lambda: met.sample(T, x0, store_chain=False, first_chain=first))
     out["rwm"] = {"metric": "banana-2D RWM chain-steps/s", "value": C * (T - 1) / t, "chains": C, "steps": T - 1,
-                  "roofline": {"bound": "fp64_simt", "achieved": 23 * C * (T - 1) / t / 1e12, "peak": fp64_peak,
-                               "unit": "TFLOP/s", "frac": 23 * C * (T - 1) / t / 1e12 / fp64_peak, "flop_per_step": 23},
+                  "roofline": {"bound": "fp64_simt", "achieved": 23 * C * (T - 1) / t / 1e12 / world, "peak": fp64_peak,
+                               "unit": "TFLOP/s", "frac": 23 * C * (T - 1) / t / 1e12 / world / fp64_peak,
+                               "flop_per_step": 23, "per": "GPU"},
                   "cpu_baseline": cpu.get("rwm")}
     # C5: camel-8D HMC, ELM Gaussian-basis surrogate gradient, 1e5 chains x 20 leapfrog
     rs = np.random.default_rng(0)
@@ -369,8 +386,9 @@ def other_workloads(H, _lib, torch, fp64_peak, with_cpu):
             H.surrogate.attach_surrogate_gradient(tgt, basis, params, 0.0, w)
             upd = H.hamiltonian.HamiltonianUpdate(tgt, H.densities.Gaussian(8), 20, 0.01, precision=prec)
             Ch, Th = 100_000, 3
-            x0h = torch.full((Ch, 8), 1 / 3, device="cuda", dtype=torch.float64)
-            t = timed(lambda: upd.sample(Th, x0h, store_chain=False), reps=2)
+            first, cnt = parallel.item_span(Ch, rank, world)
+            x0h = torch.full((cnt, 8), 1 / 3, device="cuda", dtype=torch.float64)
+            t = timed(lambda: upd.sample(Th, x0h, store_chain=False, first_chain=first), reps=2)
             flop = 21 * (4 * nodes * 8 + 5 * nodes + 4 * 8) + 20 * 64 + 72 + 48
             out["hmc_elm%d_%s" % (nodes, prec)] = {
                 "metric": "camel-8D HMC+ELM chain-steps/s", "value": Ch * (Th - 1) / t, "nodes": nodes,
