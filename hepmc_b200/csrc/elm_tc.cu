@@ -3,9 +3,9 @@
 //   hmc_tc_kernel      : HMC ensembles (hepmc_hmc_chains, precision = 2): momentum draw,
 //                        leapfrog and the float64 Metropolis test stay per-thread exactly as in
 //                        chains.cu; every gradient evaluation is a CTA-collective GEMM pipeline.
-// Block = 128 owner threads (one chain = one TMEM lane each) + 128 helper threads (exp of the
-// upper half of the S columns) + one MMA-issuing warp;
-// persistent over tiles of 128 chains; node tables are built once per CTA.
+// Block = two independent groups, each 128 owner threads (one chain = one TMEM lane) + one
+// MMA-issuing warp (see elm_tc.cuh); every group is persistent over its own tiles of 128 chains;
+// node tables are built once per CTA and shared.
 #include "chains.cuh"
 #include "elm_tc.cuh"
 
@@ -25,14 +25,18 @@ __device__ __forceinline__ TcSetup tc_prologue(unsigned char* smem, const hepmc_
     u.n_node_tiles = (elm.nodes + TILE_N - 1) / TILE_N;
     u.s = carve_tc(smem, u.n_node_tiles);
     u.bars = smem_u32(u.s.bars);
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
     if (warp == MMA_WARP) tmem_alloc(smem_u32(u.s.tmem_ptr), TMEM_COLS);
     if (threadIdx.x == 0) {
-        mbar_init(u.bars + 8 * BAR_A, N_OWNER / 32);
-        mbar_init(u.bars + 8 * BAR_D2, 1);
-        for (int b = 0; b < N_SBUF; ++b) {
-            mbar_init(u.bars + 8 * (BAR_S0 + b), 1);
-            mbar_init(u.bars + 8 * (BAR_P0 + b), N_COMPUTE / 32);
+        for (int g = 0; g < N_GROUPS; ++g) {
+            const uint32_t gb = u.bars + 8 * N_BARS * g;
+            mbar_init(gb + 8 * BAR_A, N_OWNER / 32);
+            mbar_init(gb + 8 * BAR_D2, N_ISS);
+            for (int b = 0; b < N_SBUF; ++b) {
+                mbar_init(gb + 8 * (BAR_S0 + b), 1);
+                mbar_init(gb + 8 * (BAR_P0 + b), N_OWNER / 32);
+                mbar_init(gb + 8 * (BAR_G0 + b), N_ISS > 1 ? N_ISS - 1 : 1);
+            }
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -50,7 +54,7 @@ __device__ __forceinline__ TcSetup tc_prologue(unsigned char* smem, const hepmc_
 __device__ __forceinline__ void tc_epilogue(const TcSetup& u) {
     fence_before();
     __syncthreads();
-    if ((threadIdx.x >> 5) == MMA_WARP) tmem_dealloc(u.tmem_base, TMEM_COLS);
+    if (__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == MMA_WARP) tmem_dealloc(u.tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ stand-alone gradient
@@ -60,31 +64,35 @@ __global__ void __launch_bounds__(N_THREADS, 1) elm_grad_tc_kernel(const __grid_
                                                                    double* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_tc[];
     const TcSetup u = tc_prologue<D>(smem_tc, elm);
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
     const int64_t n_tiles = (n + TILE_M - 1) / TILE_M;
-    if (warp < TILE_M / 32) {
+    // group of this warp; its barriers, TMEM columns and tiles (group g of CTA k: tiles 2k + g, stride 2 gridDim)
+    const int grp = warp < MMA_WARP ? warp / (N_OWNER / 32) : (warp - MMA_WARP) / N_ISS;
+    const int iss_q = warp < MMA_WARP ? 0 : (warp - MMA_WARP) % N_ISS;
+    const uint32_t gbars = u.bars + 8 * N_BARS * grp;
+    const uint32_t gtmem = u.tmem_base + GROUP_COLS * grp;
+    const int64_t tile0 = (int64_t)blockIdx.x * N_GROUPS + grp, tile_step = (int64_t)gridDim.x * N_GROUPS;
+    const int dbg = g_tc_debug;
+    if (warp < MMA_WARP) {
         ComputeState st;
-        const uint32_t lane_base = u.tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t j = tile * TILE_M + threadIdx.x;
+        const uint32_t lane_base = gtmem + ((uint32_t)((warp & 3) * 32) << 16);
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
+            const int64_t j = tile * TILE_M + (threadIdx.x & (N_OWNER - 1));
             double x[D], g[D];
 #pragma unroll
             for (int k = 0; k < D; ++k) x[k] = j < n ? xs[j * D + k] : 0.5;
-            compute_eval<D>(st, u.bars, lane_base, elm.nodes, u.n_node_tiles, x, g);
+            compute_eval<D>(st, gbars, lane_base, elm.nodes, u.n_node_tiles, dbg, x, g);
             if (j < n) {
 #pragma unroll
                 for (int k = 0; k < D; ++k) out[j * D + k] = g[k];
             }
         }
-    } else if (warp < MMA_WARP) {
-        ComputeState st;
-        const uint32_t lane_base = u.tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-            exp_half_tiles(st, u.bars, lane_base, elm.nodes, u.n_node_tiles, 1);
-    } else if (threadIdx.x == N_COMPUTE) {
+    } else {   // issuing warps: all lanes run the loop, one elected lane issues each instruction
         IssuerState st;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-            issuer_eval(st, u.bars, u.tmem_base, u.b1_saddr, u.b2_saddr, elm.nodes, u.n_node_tiles);
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
+            if (iss_q == 0) issuer_eval(st, gbars, gtmem, u.b1_saddr, u.b2_saddr, elm.nodes, u.n_node_tiles, dbg);
+            else aux_issuer_eval(st, gbars, gtmem, u.b2_saddr, elm.nodes, u.n_node_tiles, iss_q, dbg);
+        }
     }
     tc_epilogue(u);
 }
@@ -98,18 +106,28 @@ __global__ void __launch_bounds__(N_THREADS, 1) hmc_tc_kernel(const __grid_const
                                                               const __grid_constant__ ChainArgs a) {
     extern __shared__ __align__(128) unsigned char smem_tc[];
     const TcSetup u = tc_prologue<NDIM>(smem_tc, elm);
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
     const int64_t n_tiles = (a.n_chains + TILE_M - 1) / TILE_M;
     const int64_t evals_per_tile = (a.T - 1) * (int64_t)(a.steps + 1);
-    if (warp < TILE_M / 32) {
+    const int grp = warp < MMA_WARP ? warp / (N_OWNER / 32) : (warp - MMA_WARP) / N_ISS;
+    const int iss_q = warp < MMA_WARP ? 0 : (warp - MMA_WARP) % N_ISS;
+    const uint32_t gbars = u.bars + 8 * N_BARS * grp;
+    const uint32_t gtmem = u.tmem_base + GROUP_COLS * grp;
+    int64_t tile0 = (int64_t)blockIdx.x * N_GROUPS + grp, tile_step = (int64_t)gridDim.x * N_GROUPS;
+    const int dbg = g_tc_debug;
+    if ((dbg & 32) && grp == 1) tile0 = n_tiles;   // development knob: group 1 idle
+    if (warp < MMA_WARP) {
         ComputeState cs;
-        const uint32_t lane_base = u.tmem_base + ((uint32_t)(warp * 32) << 16);
+#ifdef HEPMC_TC_TRACE
+        if (threadIdx.x == 0 && blockIdx.x == 0) cs.trp = g_tc_trace;
+#endif
+        const uint32_t lane_base = gtmem + ((uint32_t)((warp & 3) * 32) << 16);
         const PhiloxKey key = philox_expand(a.seed);
         constexpr int NCALL = (NDIM + 1) / 2;
         constexpr uint32_t CPS = NCALL + 1;
         const double half_eps = a.step_size / 2;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t c = tile * TILE_M + threadIdx.x;
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
+            const int64_t c = tile * TILE_M + (threadIdx.x & (N_OWNER - 1));
             const bool active = c < a.n_chains;
             const uint64_t g = (uint64_t)(a.first_chain + c);
             int64_t acc = 0;
@@ -137,13 +155,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) hmc_tc_kernel(const __grid_const
                 }
 #pragma unroll
                 for (int d = 0; d < NDIM; ++d) { q[d] = x[d]; p[d] = p0[d]; }
-                compute_eval<NDIM>(cs, u.bars, lane_base, elm.nodes, u.n_node_tiles, q, grad);
+                compute_eval<NDIM>(cs, gbars, lane_base, elm.nodes, u.n_node_tiles, dbg, q, grad);
                 for (int s = 0; s < a.steps; ++s) {
 #pragma unroll
                     for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
 #pragma unroll
                     for (int d = 0; d < NDIM; ++d) q[d] += a.step_size * (pdist.c[d] * (p[d] - pdist.a[d]));
-                    compute_eval<NDIM>(cs, u.bars, lane_base, elm.nodes, u.n_node_tiles, q, grad);
+                    compute_eval<NDIM>(cs, gbars, lane_base, elm.nodes, u.n_node_tiles, dbg, q, grad);
 #pragma unroll
                     for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
                 }
@@ -178,17 +196,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) hmc_tc_kernel(const __grid_const
             }
             finish_counts(a, active, c, acc);
         }
-    } else if (warp < MMA_WARP) {
-        ComputeState hs;
-        const uint32_t lane_base = u.tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-            for (int64_t e = 0; e < evals_per_tile; ++e)
-                exp_half_tiles(hs, u.bars, lane_base, elm.nodes, u.n_node_tiles, 1);
-    } else if (threadIdx.x == N_COMPUTE) {
+    } else {   // issuing warps: all lanes run the loop, one elected lane issues each instruction
         IssuerState st;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-            for (int64_t e = 0; e < evals_per_tile; ++e)
-                issuer_eval(st, u.bars, u.tmem_base, u.b1_saddr, u.b2_saddr, elm.nodes, u.n_node_tiles);
+#ifdef HEPMC_TC_TRACE
+        if (grp == 0 && iss_q == 0 && blockIdx.x == 0) st.trp = g_tc_trace;
+#endif
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step)
+            for (int64_t e = 0; e < evals_per_tile; ++e) {
+                if (iss_q == 0) issuer_eval(st, gbars, gtmem, u.b1_saddr, u.b2_saddr, elm.nodes, u.n_node_tiles, dbg);
+                else aux_issuer_eval(st, gbars, gtmem, u.b2_saddr, elm.nodes, u.n_node_tiles, iss_q, dbg);
+            }
     }
     tc_epilogue(u);
 }
@@ -212,6 +229,12 @@ static int tc_common_checks(const hepmc_elm_t& elm, int ndim, size_t& smem) {
         default: break;                                                                         \
     }
 
+#ifdef HEPMC_TC_TRACE
+extern "C" int hepmc_tc_trace(long long* buf_dev) {
+    return (int)cudaMemcpyToSymbol(tc::g_tc_trace, &buf_dev, sizeof(buf_dev));
+}
+#endif
+
 extern "C" int hepmc_tc_debug(int mode) {
     return (int)cudaMemcpyToSymbol(tc::g_tc_debug, &mode, sizeof(int));
 }
@@ -221,7 +244,8 @@ int launch_elm_grad_tc(const hepmc_elm_t& elm, int ndim, const double* xs, int64
     int e = tc_common_checks(elm, ndim, smem);
     if (e) return e;
     const int64_t tiles = (n + tc::TILE_M - 1) / tc::TILE_M;
-    const unsigned blocks = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+    const int64_t pairs = (tiles + tc::N_GROUPS - 1) / tc::N_GROUPS;
+    const unsigned blocks = (unsigned)(pairs < sm_count() ? pairs : sm_count());
 #define GRAD_TC_CASE(ND)                                                                                           \
     do {                                                                                                           \
         HEPMC_CUDA(cudaFuncSetAttribute(elm_grad_tc_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -238,7 +262,8 @@ int launch_hmc_tc(const Dens& dens, const Dens& pdist, const hepmc_elm_t& elm, c
     int e = tc_common_checks(elm, dens.ndim, smem);
     if (e) return e;
     const int64_t tiles = (a.n_chains + tc::TILE_M - 1) / tc::TILE_M;
-    const unsigned blocks = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+    const int64_t pairs = (tiles + tc::N_GROUPS - 1) / tc::N_GROUPS;
+    const unsigned blocks = (unsigned)(pairs < sm_count() ? pairs : sm_count());
 #define HMC_TC_CASE(ND)                                                                                            \
     do {                                                                                                           \
         HEPMC_CUDA(cudaFuncSetAttribute(hmc_tc_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -17,35 +17,57 @@
 //           grad_jk = D2_jk - x'_jk * D2_jD
 // Both GEMMs take A from TMEM (tcgen05.mma [d], [a], b_desc) and B from shared memory in the
 // canonical K-major no-swizzle layout; node tables for all tiles stay resident in smem
-// (B1: 16 KB, B2: 8 KB per 128 nodes).  One CTA = 128 chains (TMEM lanes) = 4 compute warps +
-// 4 helper warps (upper half of the S columns) + 1 MMA-issuing warp; S is double buffered in TMEM so GEMM-1 of node tile t+1 / GEMM-2 of tile t
-// overlap the exponentials of the tiles in between.  mbarrier pipeline:
-//   A_ready (128 arrivals) -> [G1(0), G1(1)] -> S_full[b] (commit) -> exp -> P_ready[b] (256)
-//   -> G2(t), G1(t+2) ... -> D2_full (commit) -> epilogue.
+// (B1: 8 KB, B2: 4 KB per 64 nodes).
+//
+// One CTA runs TWO independent pipelines ("groups"), each = 128 chains (TMEM lanes 0..127, its own
+// 256 TMEM columns and mbarriers) = 4 owner warps + 1 MMA-issuing warp, sharing only the node
+// tables, the MUFU and the tensor pipe.  HMC evaluates its gradients strictly one after the other,
+// and one evaluation is a chain of ~10 hand-offs (A1 -> G1 -> S_full -> exp -> P_ready -> G2 ->
+// D2_full -> epilogue -> leapfrog) of ~500 cycles each: a single pipeline spends 5-7 k cycles per
+// evaluation waiting (measured: 7.2 k cycles for a ONE-tile evaluation).  Two groups fill each
+// other's bubbles.  A tcgen05.mma costs its issuing thread 55-80 cycles whatever its N
+// (scripts/tc_microbench.cu: 16 x (M128 N16 K8) = 900 cycles from one thread; a second thread
+// issues another 16 in the same time), so the 12 MMAs of a 64-node tile (4 GEMM-1 + 8 GEMM-2)
+// are spread over N_ISS issuing threads per group: issuer 0 does GEMM-1 and its share of the
+// GEMM-2 K-steps, the others only GEMM-2, each into its own D2 accumulator (summed in the epilogue).
+// Per group S is triple buffered in TMEM (64 columns each) so GEMM-1 of node tile t+2 / GEMM-2 of
+// tile t overlap the exponentials of the tiles in between.  mbarrier pipeline per group:
+//   A_ready (4 warps) -> [G1(0..2)] -> S_full[b] (commit) -> exp -> P_ready[b] (4 warps)
+//   -> every issuer: its K-steps of G2(t); issuers > 0 commit G2_done[b]
+//   -> issuer 0: G1(t+3) once G2_done[b] says S[b] is no longer read ... -> D2_full (N_ISS commits) -> epilogue.
 #pragma once
 #include "common.cuh"
 
 namespace hepmc {
 namespace tc {
 
-constexpr int TILE_M = 128;      // chains per CTA tile (TMEM lanes)
-constexpr int TILE_N = 128;      // nodes per tile
+constexpr int TILE_M = 128;      // chains per group tile (TMEM lanes)
+constexpr int TILE_N = 64;       // nodes per tile
 constexpr int K1 = 32;           // 3 * (D + 2) padded to a multiple of 8, D <= 8
 constexpr int N2 = 16;           // D + 1 padded to the MMA N granularity at M = 128
 constexpr int MAX_D = 8;
-constexpr int N_ACC = 1;          // GEMM-2 accumulators (round-robin over 2 or 4 measured: no gain, a tcgen05.mma costs ~100 cycles here)
-constexpr int N_SBUF = 3;         // S/P tiles in flight: the commit -> mbarrier -> waiter round trip is ~1000 cycles
-constexpr int COL_A1 = 0, COL_D2 = 32, COL_S0 = 64, TMEM_COLS = 512;   // S buffer b at COL_S0 + 128 b
+constexpr int N_GROUPS = 2;      // independent pipelines per CTA
+#ifndef HEPMC_TC_ISSUERS
+#define HEPMC_TC_ISSUERS 1
+#endif
+constexpr int N_ISS = HEPMC_TC_ISSUERS;   // MMA-issuing threads per group; issuer q owns K-steps q, q + N_ISS, ... of GEMM-2
+constexpr int N_SBUF = 3;        // S/P tiles in flight per group
+constexpr int GROUP_COLS = 256;  // TMEM columns per group
+constexpr int COL_A1 = 0, COL_D2 = 32, COL_S0 = 64, TMEM_COLS = 512;   // per group; S buffer b at COL_S0 + TILE_N b
 constexpr int B1_TILE_BYTES = (K1 / 4) * TILE_N * 16;   // [K chunk][node row][16 B]
 constexpr int B2_TILE_BYTES = (TILE_N / 4) * N2 * 16;   // [node chunk][n row][16 B]
-constexpr int N_OWNER = TILE_M;                         // owner threads: one chain = one TMEM lane each
-constexpr int N_COMPUTE = 2 * TILE_M;                   // + helper warps: same lanes, upper half of the S columns
-constexpr int N_THREADS = N_COMPUTE + 32;               // + MMA / allocator warp
+constexpr int N_OWNER = TILE_M;                         // owner threads per group: one chain = one TMEM lane each
+constexpr int N_COMPUTE = N_GROUPS * TILE_M;            // owner threads of all groups
+constexpr int N_THREADS = N_COMPUTE + 32 * N_GROUPS * N_ISS;   // + MMA-issuing warps (the first allocates TMEM)
 constexpr int MMA_WARP = N_COMPUTE / 32;
+constexpr int N_BARS = 2 + 3 * N_SBUF;                  // mbarriers per group
+static_assert(N_ISS == 1 || N_ISS == 2, "issuers must divide the 2 K-steps of the narrowest tile");
+static_assert(COL_D2 + N_ISS * N2 <= COL_S0, "TMEM column plan");
+static_assert(COL_S0 + N_SBUF * TILE_N <= GROUP_COLS && N_GROUPS * GROUP_COLS <= TMEM_COLS, "TMEM column plan");
 
 __host__ __device__ inline size_t smem_bytes(int nodes) {
     const int nt = (nodes + TILE_N - 1) / TILE_N;
-    return (size_t)nt * (B1_TILE_BYTES + B2_TILE_BYTES) + 128;
+    return (size_t)nt * (B1_TILE_BYTES + B2_TILE_BYTES) + 256;
 }
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -57,7 +79,22 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#ifndef HEPMC_TC_SPIN
+#define HEPMC_TC_SPIN 1
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if HEPMC_TC_SPIN
+    // non-blocking poll: the suspended form (try_wait) was measured to add ~0.5 us per hand-off
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+#else
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
@@ -67,6 +104,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}" ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -79,33 +117,32 @@ __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// The MMA-issuing warps run their loops with ALL 32 lanes (warp-uniform control flow and operands)
+// and elect one lane per instruction inside the asm block.  Issuing from a single-lane branch
+// (if (threadIdx.x == ...)) makes ptxas wrap every tcgen05.mma in an ELECT / 6 x R2UR.BROADCAST /
+// BRA.U.ANY waterfall loop, because it cannot prove the operands warp-uniform: measured 55-130
+// cycles per MMA for the issuing thread instead of the ~10 the uniform datapath needs.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[tmem] . B[smem desc]^T, TF32 operands, FP32 accumulate
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                             uint32_t accumulate) {
     asm volatile(
         "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+        ".reg .pred e;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}" ::"r"(bar) : "memory");
 }
-
-// Same, descriptor passed as (lo, hi) words and the accumulate flag as a compile-time constant:
-// the issuing thread is a single lane, so every scalar instruction per MMA is ~5 cycles of
-// issue latency -- the descriptor is advanced with ONE 32-bit add per MMA.
+// D[tmem] (+)= A[tmem] . B[smem desc]^T, TF32 operands, FP32 accumulate; descriptor passed as
+// (lo, hi) words (advanced with ONE 32-bit add per MMA), accumulate flag a compile-time constant
 template <int ACC>
 __device__ __forceinline__ void umma_tf32_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi,
                                                 uint32_t idesc) {
     asm volatile(
         "{\n"
-        ".reg .pred p;\n"
+        ".reg .pred p, e;\n"
         ".reg .b64 bd;\n"
         "setp.ne.b32 p, %5, 0;\n"
         "mov.b64 bd, {%2, %3};\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n"
         "}" ::"r"(d_tmem), "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "n"(ACC) : "memory");
 }
 
@@ -170,13 +207,31 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 }
 
 // development knob (scripts only): 1 = skip GEMM-2, 2 = skip exp, 4 = GEMM-2 with 2 MMAs per tile,
-// 8 = GEMM-1 with 1 MMA per tile, 16 = exp stage without TMEM access
+// 8 = GEMM-1 with 1 MMA per tile, 16 = exp stage without TMEM access, 32 = group 1 idle.
+// Read ONCE per kernel into a register: every tcgen05 asm statement is a compiler memory barrier,
+// so reading the global inside the issue loops cost a ~200-cycle load per use (measured with
+// the trace below: 110 instead of 55 cycles per issued MMA).
 __device__ int g_tc_debug = 0;
+
+// development trace (make EXTRA=-DHEPMC_TC_TRACE): clock64 stamps of the hand-offs of group 0 of
+// CTA 0; owner thread 0 writes records [0, 4096), the issuer [4096, 8192): (code, tile, clock)
+#ifdef HEPMC_TC_TRACE
+__device__ long long* g_tc_trace = nullptr;
+#define HEPMC_TRACE(st, base, code, tile)                                                      \
+    do {                                                                                       \
+        if ((st).trp && (threadIdx.x & 31) == 0 && (st).tr < 1360) {                                                      \
+            long long* r_ = (st).trp + 3 * ((base) + (st).tr++);                               \
+            r_[0] = (code); r_[1] = (tile); r_[2] = clock64();                                 \
+        }                                                                                      \
+    } while (0)
+#else
+#define HEPMC_TRACE(st, base, code, tile) do { } while (0)
+#endif
 
 struct Shared {
     float* b1;           // [n_tiles][K1/4][TILE_N][4]
     float* b2;           // [n_tiles][TILE_N/4][N2][4]
-    uint64_t* bars;      // A_ready, S_full[2], P_ready[2], D2_full
+    uint64_t* bars;      // per group: A_ready, D2_full, S_full[N_SBUF], P_ready[N_SBUF]
     uint32_t* tmem_ptr;
 };
 
@@ -185,11 +240,12 @@ __device__ __forceinline__ Shared carve_tc(unsigned char* base, int n_tiles) {
     s.b1 = reinterpret_cast<float*>(base);
     s.b2 = reinterpret_cast<float*>(base + (size_t)n_tiles * B1_TILE_BYTES);
     s.bars = reinterpret_cast<uint64_t*>(base + (size_t)n_tiles * (B1_TILE_BYTES + B2_TILE_BYTES));
-    s.tmem_ptr = reinterpret_cast<uint32_t*>(s.bars + 2 + 2 * N_SBUF);
+    s.tmem_ptr = reinterpret_cast<uint32_t*>(s.bars + N_GROUPS * N_BARS);
     return s;
 }
 
-enum { BAR_A = 0, BAR_D2 = 1, BAR_S0 = 2, BAR_P0 = 2 + N_SBUF };   // S_full[b] = BAR_S0 + b, P_ready[b] = BAR_P0 + b
+// S_full[b] = BAR_S0 + b, P_ready[b] = BAR_P0 + b, G2_done[b] = BAR_G0 + b (indices within a group's N_BARS barriers)
+enum { BAR_A = 0, BAR_D2 = 1, BAR_S0 = 2, BAR_P0 = 2 + N_SBUF, BAR_G0 = 2 + 2 * N_SBUF };
 
 // Build the resident node tables (all threads).  centers (I, D), widths (I,), out_w (I,).
 template <int D>
@@ -246,13 +302,17 @@ __device__ __forceinline__ void build_tables(const Shared& s, const double* __re
     }
 }
 
-// ---- MMA-issuer side: one gradient evaluation over all node tiles (one elected thread) ----
+// ---- MMA-issuer side: one gradient evaluation of one group over all node tiles (one elected thread).
+// `tmem_base` and `bars` are the group's.
 struct IssuerState {
     uint32_t ph_a = 0;
     uint32_t ph_p[N_SBUF] = {};
+    uint32_t ph_g[N_SBUF] = {};
+    int tr = 0;                 // trace cursor
+    long long* trp = nullptr;   // trace buffer (NULL: not traced)
 };
 
-__device__ __forceinline__ void issue_g1(uint32_t tmem_base, uint32_t b1_saddr, int t, int n_cols) {
+__device__ __forceinline__ void issue_g1(uint32_t tmem_base, uint32_t b1_saddr, int t, int n_cols, int dbg) {
     const uint32_t d = tmem_base + COL_S0 + (t % N_SBUF) * TILE_N;
     const uint32_t idesc = make_idesc(TILE_M, n_cols);
     const uint64_t bd0 = make_desc(b1_saddr + t * B1_TILE_BYTES, TILE_N * 16, 128);
@@ -260,44 +320,49 @@ __device__ __forceinline__ void issue_g1(uint32_t tmem_base, uint32_t b1_saddr, 
     const uint32_t a = tmem_base + COL_A1;
     constexpr uint32_t STEP = (2 * TILE_N * 16) >> 4;   // two 16-byte K chunks per MMA, in descriptor units
     umma_tf32_ts_lh<0>(d, a, lo, hi, idesc);
-    if (g_tc_debug & 8) return;
+    if (dbg & 8) return;
 #pragma unroll
     for (int ks = 1; ks < K1 / 8; ++ks) umma_tf32_ts_lh<1>(d, a + ks * 8, lo + ks * STEP, hi, idesc);
 }
-__device__ __forceinline__ void issue_g2(uint32_t tmem_base, uint32_t b2_saddr, int t, int n_cols, bool first) {
+// K-steps q, q + N_ISS, ... of GEMM-2 of tile t into issuer q's accumulator
+__device__ __forceinline__ void issue_g2(uint32_t tmem_base, uint32_t b2_saddr, int t, int n_cols, bool first, int q, int dbg) {
     const uint32_t a = tmem_base + COL_S0 + (t % N_SBUF) * TILE_N;
-    const uint32_t d = tmem_base + COL_D2;
+    const uint32_t d = tmem_base + COL_D2 + q * N2;
     const uint32_t idesc = make_idesc(TILE_M, N2);
     const uint64_t bd0 = make_desc(b2_saddr + t * B2_TILE_BYTES, N2 * 16, 128);
     const uint32_t lo = (uint32_t)bd0, hi = (uint32_t)(bd0 >> 32);
     constexpr uint32_t STEP = (2 * N2 * 16) >> 4;
-    const int nk = (g_tc_debug & 4) ? 2 : (n_cols >> 3);
+    const int nk = (dbg & 4) ? N_ISS : (n_cols >> 3);
 #pragma unroll
-    for (int ks = 0; ks < TILE_N / 8; ++ks) {
+    for (int j = 0; j < TILE_N / 8 / N_ISS; ++j) {
+        const int ks = j * N_ISS + q;
         if (ks < nk) {
-            const uint32_t dq = d + (ks % N_ACC) * N2;
-            if (first && ks < N_ACC) umma_tf32_ts_lh<0>(dq, a + ks * 8, lo + ks * STEP, hi, idesc);
-            else umma_tf32_ts_lh<1>(dq, a + ks * 8, lo + ks * STEP, hi, idesc);
+            if (first && j == 0) umma_tf32_ts_lh<0>(d, a + ks * 8, lo + ks * STEP, hi, idesc);
+            else umma_tf32_ts_lh<1>(d, a + ks * 8, lo + ks * STEP, hi, idesc);
         }
     }
 }
 
 // node-tile widths: full tiles are TILE_N; the last one is padded up to a multiple of 16
+// (padding nodes have P = 0 and B2 = 0)
 __device__ __forceinline__ int tile_cols(int nodes, int t) {
     const int rem = nodes - t * TILE_N;
     return rem >= TILE_N ? TILE_N : ((rem + 15) & ~15);
 }
 
 __device__ __forceinline__ void issuer_eval(IssuerState& st, uint32_t bars, uint32_t tmem_base, uint32_t b1_saddr,
-                                            uint32_t b2_saddr, int nodes, int n_tiles) {
+                                            uint32_t b2_saddr, int nodes, int n_tiles, int dbg) {
+    HEPMC_TRACE(st, 4096, 10, -1);
     mbar_wait(bars + 8 * BAR_A, st.ph_a);
     st.ph_a ^= 1;
     fence_after();
+    HEPMC_TRACE(st, 4096, 11, -1);
 #pragma unroll
     for (int b = 0; b < N_SBUF; ++b) {
         if (b < n_tiles) {
-            issue_g1(tmem_base, b1_saddr, b, tile_cols(nodes, b));
+            issue_g1(tmem_base, b1_saddr, b, tile_cols(nodes, b), dbg);
             umma_commit(bars + 8 * (BAR_S0 + b));
+            HEPMC_TRACE(st, 4096, 12, b);
         }
     }
     for (int t = 0; t < n_tiles; ++t) {
@@ -305,38 +370,71 @@ __device__ __forceinline__ void issuer_eval(IssuerState& st, uint32_t bars, uint
         mbar_wait(bars + 8 * (BAR_P0 + b), st.ph_p[b]);
         st.ph_p[b] ^= 1;
         fence_after();
-        if (!(g_tc_debug & 1)) issue_g2(tmem_base, b2_saddr, t, tile_cols(nodes, t), t == 0);
-        if (t + N_SBUF < n_tiles) {
-            issue_g1(tmem_base, b1_saddr, t + N_SBUF, tile_cols(nodes, t + N_SBUF));
-            umma_commit(bars + 8 * (BAR_S0 + b));
+        HEPMC_TRACE(st, 4096, 13, t);
+        if (!(dbg & 1)) issue_g2(tmem_base, b2_saddr, t, tile_cols(nodes, t), t == 0, 0, dbg);
+        HEPMC_TRACE(st, 4096, 14, t);
+        if (N_ISS == 1) {
+            if (t + N_SBUF < n_tiles) {   // same thread: G1(t+3) is ordered behind G2(t), which reads S[b]
+                issue_g1(tmem_base, b1_saddr, t + N_SBUF, tile_cols(nodes, t + N_SBUF), dbg);
+                umma_commit(bars + 8 * (BAR_S0 + b));
+                HEPMC_TRACE(st, 4096, 12, t + N_SBUF);
+            }
+        } else if (t >= 1 && t - 1 + N_SBUF < n_tiles) {
+            // refill the buffer of the PREVIOUS tile: the other issuer's reads of it were committed a
+            // tile ago, so this wait does not stall the issue stream
+            const int pb = (t - 1) % N_SBUF;
+            mbar_wait(bars + 8 * (BAR_G0 + pb), st.ph_g[pb]);
+            st.ph_g[pb] ^= 1;
+            fence_after();
+            issue_g1(tmem_base, b1_saddr, t - 1 + N_SBUF, tile_cols(nodes, t - 1 + N_SBUF), dbg);
+            umma_commit(bars + 8 * (BAR_S0 + pb));
+            HEPMC_TRACE(st, 4096, 12, t - 1 + N_SBUF);
         }
+    }
+    umma_commit(bars + 8 * BAR_D2);
+    HEPMC_TRACE(st, 4096, 15, -1);
+}
+
+// issuers 1 .. N_ISS-1 of a group: their share of GEMM-2
+__device__ __forceinline__ void aux_issuer_eval(IssuerState& st, uint32_t bars, uint32_t tmem_base, uint32_t b2_saddr,
+                                                int nodes, int n_tiles, int q, int dbg) {
+    for (int t = 0; t < n_tiles; ++t) {
+        const int b = t % N_SBUF;
+        mbar_wait(bars + 8 * (BAR_P0 + b), st.ph_p[b]);
+        st.ph_p[b] ^= 1;
+        fence_after();
+        if (!(dbg & 1)) issue_g2(tmem_base, b2_saddr, t, tile_cols(nodes, t), t == 0, q, dbg);
+        if (t + N_SBUF < n_tiles) umma_commit(bars + 8 * (BAR_G0 + b));   // S[b] will be refilled
     }
     umma_commit(bars + 8 * BAR_D2);
 }
 
-// ---- compute side: thread = chain = TMEM lane ----
+// ---- compute side: thread = chain = TMEM lane; `bars` and the column part of `tmem_lane_base` are the group's ----
 struct ComputeState {
     uint32_t ph_s[N_SBUF] = {};
     uint32_t ph_d2 = 0;
+    int tr = 0;                 // trace cursor
+    long long* trp = nullptr;   // trace buffer (NULL: not traced)
 };
 
-// S -> P = exp2(S) in place for one half (64 columns) of every node tile of one gradient
-// evaluation.  half 0: owner warps, half 1: helper warps (same TMEM lanes, warp % 4 equal).
-__device__ __forceinline__ void exp_half_tiles(ComputeState& st, uint32_t bars, uint32_t tmem_lane_base, int nodes,
-                                               int n_tiles, int half) {
+// Plain form of exp_tiles (one tile after the other, every wait exposed): kept for the development
+// knobs (skip exp / MUFU without TMEM) and as the readable statement of the protocol.
+__device__ __forceinline__ void exp_tiles_simple(ComputeState& st, uint32_t bars, uint32_t tmem_lane_base, int nodes,
+                                          int n_tiles, int dbg) {
     for (int t = 0; t < n_tiles; ++t) {
         const int b = t % N_SBUF;
-        const uint32_t col = COL_S0 + b * TILE_N + half * 64;
+        const uint32_t col = COL_S0 + b * TILE_N;
+        HEPMC_TRACE(st, 0, 1, t);
         mbar_wait(bars + 8 * (BAR_S0 + b), st.ph_s[b]);
         st.ph_s[b] ^= 1;
         fence_after();
-        const int my_cols = tile_cols(nodes, t) - half * 64;   // columns of this half that GEMM-2 reads
-        if (my_cols > 0 && !(g_tc_debug & 2)) {
+        HEPMC_TRACE(st, 0, 2, t);
+        if (!(dbg & 2)) {
             // software pipeline over 16-column chunks: the TMEM read of chunk c+1 is in flight
-            // while the MUFU works on chunk c (TMEM read and MUFU both run at 4 values/clk/SMSP)
-            const int nch = my_cols >= 64 ? 4 : (my_cols >> 4);
+            // while the MUFU works on chunk c
+            const int nch = tile_cols(nodes, t) >> 4;
             uint32_t va[16], vb[16];
-            if (g_tc_debug & 16) {  // experiment: MUFU work without touching TMEM
+            if (dbg & 16) {  // experiment: MUFU work without touching TMEM
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { va[j] = threadIdx.x + j; vb[j] = threadIdx.x * 3 + j; }
                 for (int c = 0; c < nch; ++c) {
@@ -345,37 +443,99 @@ __device__ __forceinline__ void exp_half_tiles(ComputeState& st, uint32_t bars, 
                 }
                 if (va[3] == 0x12345u) tmem_st16(tmem_lane_base + col, va);
             } else {
-            tmem_ld16(tmem_lane_base + col, va);
-            tmem_wait_ld();
+                tmem_ld16(tmem_lane_base + col, va);
+                tmem_wait_ld();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c < nch) {
-                    if (c & 1) {
-                        if (c + 1 < nch) tmem_ld16(tmem_lane_base + col + (c + 1) * 16, va);
+                for (int c = 0; c < TILE_N / 16; ++c) {
+                    if (c < nch) {
+                        if (c & 1) {
+                            if (c + 1 < nch) tmem_ld16(tmem_lane_base + col + (c + 1) * 16, va);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) vb[j] = __float_as_uint(ex2_approx(__uint_as_float(vb[j])));
-                        tmem_st16(tmem_lane_base + col + c * 16, vb);
-                    } else {
-                        if (c + 1 < nch) tmem_ld16(tmem_lane_base + col + (c + 1) * 16, vb);
+                            for (int j = 0; j < 16; ++j) vb[j] = __float_as_uint(ex2_approx(__uint_as_float(vb[j])));
+                            tmem_st16(tmem_lane_base + col + c * 16, vb);
+                        } else {
+                            if (c + 1 < nch) tmem_ld16(tmem_lane_base + col + (c + 1) * 16, vb);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) va[j] = __float_as_uint(ex2_approx(__uint_as_float(va[j])));
-                        tmem_st16(tmem_lane_base + col + c * 16, va);
+                            for (int j = 0; j < 16; ++j) va[j] = __float_as_uint(ex2_approx(__uint_as_float(va[j])));
+                            tmem_st16(tmem_lane_base + col + c * 16, va);
+                        }
+                        if (c + 1 < nch) tmem_wait_ld();
                     }
-                    if (c + 1 < nch) tmem_wait_ld();
                 }
-            }
             }
             tmem_wait_st();
         }
         fence_before();
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(bars + 8 * (BAR_P0 + b));  // one arrival per warp
+        HEPMC_TRACE(st, 0, 3, t);
     }
+}
+
+// S -> P = exp2(S) in place for every node tile of one gradient evaluation (64 columns per tile
+// and TMEM lane), as ONE stream of 16-column chunks across tile boundaries: the TMEM read of the
+// next chunk, the poll of the next tile's S_full and the wait::st / P_ready arrival of the
+// previous tile are all issued right after a batch of 16 MUFU.EX2 (128 cycles of MUFU time), so
+// none of those latencies is exposed (measured with the trace: ~400 cycles per tile before).
+__device__ __forceinline__ void exp_tiles(ComputeState& st, uint32_t bars, uint32_t tmem_lane_base, int nodes,
+                                          int n_tiles, int dbg) {
+    if (dbg & 18) {
+        exp_tiles_simple(st, bars, tmem_lane_base, nodes, n_tiles, dbg);
+        return;
+    }
+    uint32_t va[16], vb[16];
+    HEPMC_TRACE(st, 0, 1, 0);
+    mbar_wait(bars + 8 * BAR_S0, st.ph_s[0]);
+    st.ph_s[0] ^= 1;
+    fence_after();
+    HEPMC_TRACE(st, 0, 2, 0);
+    tmem_ld16(tmem_lane_base + COL_S0, va);
+    int prev_b = -1;   // tile whose P_ready arrival is still owed
+    for (int t = 0; t < n_tiles; ++t) {
+        const int b = t % N_SBUF;
+        const uint32_t col = COL_S0 + b * TILE_N;
+        const int nch = tile_cols(nodes, t) >> 4;
+        const bool more = t + 1 < n_tiles;        // full tile (nch == 4) whenever another one follows
+        const int nb = (t + 1) % N_SBUF;
+#pragma unroll
+        for (int c = 0; c < TILE_N / 16; ++c) {
+            if (c < nch) {
+                uint32_t(&cur)[16] = (c & 1) ? vb : va;
+                uint32_t(&oth)[16] = (c & 1) ? va : vb;
+                tmem_wait_ld();
+                if (c + 1 < nch) tmem_ld16(tmem_lane_base + col + (c + 1) * 16, oth);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) cur[j] = __float_as_uint(ex2_approx(__uint_as_float(cur[j])));
+                // --- in the shadow of those 16 MUFU ops ---
+                if (c == 0 && prev_b >= 0) {     // previous tile: stores done -> P_ready
+                    tmem_wait_st();
+                    fence_before();
+                    __syncwarp();
+                    if ((threadIdx.x & 31) == 0) mbar_arrive(bars + 8 * (BAR_P0 + prev_b));
+                    HEPMC_TRACE(st, 0, 3, t - 1);
+                }
+                if (c + 1 == nch && more) {      // next tile: S_full -> first chunk on its way
+                    mbar_wait(bars + 8 * (BAR_S0 + nb), st.ph_s[nb]);
+                    st.ph_s[nb] ^= 1;
+                    fence_after();
+                    HEPMC_TRACE(st, 0, 2, t + 1);
+                    tmem_ld16(tmem_lane_base + COL_S0 + nb * TILE_N, oth);
+                }
+                tmem_st16(tmem_lane_base + col + c * 16, cur);
+            }
+        }
+        prev_b = b;
+    }
+    tmem_wait_st();
+    fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bars + 8 * (BAR_P0 + prev_b));
+    HEPMC_TRACE(st, 0, 3, n_tiles - 1);
 }
 
 template <int D>
 __device__ __forceinline__ void compute_eval(ComputeState& st, uint32_t bars, uint32_t tmem_lane_base, int nodes,
-                                             int n_tiles, const double (&x)[D], double (&g)[D]) {
+                                             int n_tiles, int dbg, const double (&x)[D], double (&g)[D]) {
     // A1 row: [hi(a), hi(a), lo(a)] with a = [x', |x'|^2, 1]; single precision is enough for the
     // split (hi + lo carries 22 bits), the double -> float conversion happens once per coordinate
     uint32_t a1[32];
@@ -412,25 +572,28 @@ __device__ __forceinline__ void compute_eval(ComputeState& st, uint32_t bars, ui
             a1[2 * (D + 2) + k] = __float_as_uint(lo);
         }
     }
+    HEPMC_TRACE(st, 0, 4, -1);
     tmem_st32(tmem_lane_base + COL_A1, a1);
     tmem_wait_st();
     fence_before();
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(bars + 8 * BAR_A);  // one arrival per warp
-    exp_half_tiles(st, bars, tmem_lane_base, nodes, n_tiles, 0);
+    HEPMC_TRACE(st, 0, 5, -1);
+    exp_tiles(st, bars, tmem_lane_base, nodes, n_tiles, dbg);
     mbar_wait(bars + 8 * BAR_D2, st.ph_d2);
     st.ph_d2 ^= 1;
     fence_after();
-    uint32_t d2[N_ACC][16];
+    HEPMC_TRACE(st, 0, 6, -1);
+    uint32_t d2[N_ISS][16];
 #pragma unroll
-    for (int q = 0; q < N_ACC; ++q) tmem_ld16(tmem_lane_base + COL_D2 + q * N2, d2[q]);
+    for (int q = 0; q < N_ISS; ++q) tmem_ld16(tmem_lane_base + COL_D2 + q * N2, d2[q]);
     tmem_wait_ld();
     float acc[D + 1];
 #pragma unroll
     for (int k = 0; k <= D; ++k) {
         acc[k] = __uint_as_float(d2[0][k]);
 #pragma unroll
-        for (int q = 1; q < N_ACC; ++q) acc[k] += __uint_as_float(d2[q][k]);
+        for (int q = 1; q < N_ISS; ++q) acc[k] += __uint_as_float(d2[q][k]);
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) g[k] = (double)(acc[k] - xc[k] * acc[D]);

@@ -6,9 +6,9 @@ from hepmc_b200 import _lib
 H.set_outputs("torch")
 lib = _lib.load()
 rs = np.random.default_rng(0)
-x0h = torch.full((148 * 128, 8), 1 / 3, device="cuda", dtype=torch.float64)
-for mode in (0, 2):
-    for nodes in (128, 256, 512, 1024):
+x0h = torch.full((148 * 256, 8), 1 / 3, device="cuda", dtype=torch.float64)
+for mode in (0, 32):
+    for nodes in (128, 512, 1024):
         basis = H.surrogate.GaussianBasis(8)
         params = (rs.random((nodes, 8)), 0.01 + 0.99 * rs.random(nodes), None)
         w = 0.01 * rs.standard_normal(nodes)
@@ -20,4 +20,4 @@ for mode in (0, 2):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); upd.sample(11, x0h, store_chain=False); b.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 10
-        print("mode %2d nodes %4d: %.1f us per chain-step -> %.0f cycles per gradient eval" % (mode, nodes, ms * 1e3, ms * 1e-3 * 1.965e9 / 21))
+        print("mode %2d nodes %4d: %.1f us per chain-step -> %.0f cycles per gradient eval" % (mode, nodes, ms * 1e3, ms * 1e-3 * 1.965e9 / 21 / 2))
