@@ -80,11 +80,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 #ifndef HEPMC_TC_SPIN
-#define HEPMC_TC_SPIN 1
+#define HEPMC_TC_SPIN 0   // 1: non-blocking test_wait polling -- same hand-off latency, but the polling warps take issue slots from the exp stage
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if HEPMC_TC_SPIN
-    // non-blocking poll: the suspended form (try_wait) was measured to add ~0.5 us per hand-off
     uint32_t done;
     do {
         asm volatile(
@@ -184,6 +183,38 @@ __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// exp2 on the FMA pipe: round-to-nearest split x = xi + f, f in [-0.5, 0.5], degree-4 minimax
+// polynomial for 2^f (max relative error 2.7e-6 in float arithmetic, 200x below the TF32
+// truncation P gets in GEMM-2), exponent inserted with one integer shift-add.  9 instructions
+// per value (~11 issue slots with the surrounding moves) against one MUFU.EX2 that occupies the
+// 4-lane MUFU pipe for 8 cycles per warp: the exp stage gives POLY_MASK's share of every 16-value
+// chunk to this routine.  In isolation (scripts/exp_microbench.cu) 4-6 of 16 is the balance point
+// (300 -> 235 cycles per chunk with two warps per sub-partition); inside the pipeline issue slots
+// are scarcer and 3 of 16 is best.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -125.0f);
+    const float t = x + 12582912.0f;             // 1.5 * 2^23: xi lands in the low mantissa bits
+    const float f = x - (t - 12582912.0f);
+    float p = fmaf(0.009570102207362652f, f, 0.05591785907745361f);
+    p = fmaf(p, f, 0.240247443318367f);
+    p = fmaf(p, f, 0.6931217908859253f);
+    p = fmaf(p, f, 0.9999992847442627f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+#ifndef HEPMC_TC_POLY_MASK
+#define HEPMC_TC_POLY_MASK 0x0421   // values 0, 5, 10 of each 16-value chunk (measured optimum: 2/16 -7 %, 3/16 -8 %, 4/16 -5 %, 5/16 +2 %, 6/16 +10 % cycles)
+#endif
+template <int J>
+__device__ __forceinline__ float ex2_mixed(float x) {
+    if constexpr ((HEPMC_TC_POLY_MASK >> J) & 1) return ex2_poly(x);
+    else return ex2_approx(x);
+}
+__device__ __forceinline__ void ex2_chunk(uint32_t (&v)[16]) {
+#define HEPMC_EX2(J) v[J] = __float_as_uint(ex2_mixed<J>(__uint_as_float(v[J])));
+    HEPMC_EX2(0) HEPMC_EX2(1) HEPMC_EX2(2) HEPMC_EX2(3) HEPMC_EX2(4) HEPMC_EX2(5) HEPMC_EX2(6) HEPMC_EX2(7)
+    HEPMC_EX2(8) HEPMC_EX2(9) HEPMC_EX2(10) HEPMC_EX2(11) HEPMC_EX2(12) HEPMC_EX2(13) HEPMC_EX2(14) HEPMC_EX2(15)
+#undef HEPMC_EX2
 }
 __device__ __forceinline__ uint32_t to_tf32_rna(float x) {
     uint32_t y;
@@ -504,9 +535,8 @@ __device__ __forceinline__ void exp_tiles(ComputeState& st, uint32_t bars, uint3
                 uint32_t(&oth)[16] = (c & 1) ? va : vb;
                 tmem_wait_ld();
                 if (c + 1 < nch) tmem_ld16(tmem_lane_base + col + (c + 1) * 16, oth);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) cur[j] = __float_as_uint(ex2_approx(__uint_as_float(cur[j])));
-                // --- in the shadow of those 16 MUFU ops ---
+                ex2_chunk(cur);
+                // --- in the shadow of that batch ---
                 if (c == 0 && prev_b >= 0) {     // previous tile: stores done -> P_ready
                     tmem_wait_st();
                     fence_before();

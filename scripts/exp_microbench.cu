@@ -40,6 +40,27 @@ __global__ void __launch_bounds__(256) k(int variant, int chunks, int warps_acti
             tmem_wait_ld();
             tmem_wait_st();
             if (wa[0] == 0x1234567u) out[3] = wb[1];
+        } else if (variant == 5 || variant == 6) {
+            tmem_ld16(lane_base, va);
+            for (int c = 0; c < chunks; c += 2) {
+                tmem_wait_ld(); tmem_ld16(lane_base + ((c + 1) % 16) * 16, vb);
+                if (variant == 5) ex2_chunk(va);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) va[j] = __float_as_uint(ex2_poly(__uint_as_float(va[j])));
+                }
+                tmem_st16(lane_base + (c % 16) * 16, va);
+                tmem_wait_ld(); tmem_ld16(lane_base + ((c + 2) % 16) * 16, va);
+                if (variant == 5) ex2_chunk(vb);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) vb[j] = __float_as_uint(ex2_poly(__uint_as_float(vb[j])));
+                }
+                tmem_st16(lane_base + ((c + 1) % 16) * 16, vb);
+            }
+            tmem_wait_ld();
+            tmem_wait_st();
+            if (va[0] == 0x1234567u) out[3] = vb[1];
         } else {
             if (variant == 0 || variant == 1) tmem_ld16(lane_base, va);
             for (int c = 0; c < chunks; c += 2) {
@@ -66,9 +87,9 @@ __global__ void __launch_bounds__(256) k(int variant, int chunks, int warps_acti
 int main() {
     long long* out;
     cudaMallocManaged(&out, 64);
-    const char* names[] = {"ld16/ex2/st16", "ld16/ex2", "ex2/st16", "ex2 only", "ld32/ex2/st32"};
+    const char* names[] = {"ld16/ex2/st16", "ld16/ex2", "ex2/st16", "ex2 only", "ld32/ex2/st32", "ld16/mixed/st16", "ld16/poly/st16"};
     for (int wa : {4, 8}) {
-        for (int v = 0; v < 5; ++v) {
+        for (int v : {0, 5, 6}) {
             const int chunks = 4096;
             for (int it = 0; it < 2; ++it) {
                 k<<<148, 256>>>(v, chunks, wa, out);

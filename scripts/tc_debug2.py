@@ -7,8 +7,8 @@ H.set_outputs("torch")
 lib = _lib.load()
 rs = np.random.default_rng(0)
 x0h = torch.full((148 * 256, 8), 1 / 3, device="cuda", dtype=torch.float64)
-for mode in (0, 32):
-    for nodes in (128, 512, 1024):
+for mode in (0,):
+    for nodes in (512, 1024):
         basis = H.surrogate.GaussianBasis(8)
         params = (rs.random((nodes, 8)), 0.01 + 0.99 * rs.random(nodes), None)
         w = 0.01 * rs.standard_normal(nodes)
