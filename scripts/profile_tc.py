@@ -11,7 +11,7 @@ w = 0.01 * rs.standard_normal(nodes)
 tgt = H.densities.Camel(8)
 H.surrogate.attach_surrogate_gradient(tgt, basis, params, 0.0, w)
 upd = H.hamiltonian.HamiltonianUpdate(tgt, H.densities.Gaussian(8), 20, 0.01, precision="tc")
-x0h = torch.full((148 * 128, 8), 1 / 3, device="cuda", dtype=torch.float64)
+x0h = torch.full((148 * 256, 8), 1 / 3, device="cuda", dtype=torch.float64)
 for _ in range(2):
     upd.sample(2, x0h, store_chain=False)
 torch.cuda.synchronize()
