@@ -254,7 +254,15 @@ def run_b200(args):
                      "flop_per_point": FLOP_PER_POINT,
                      "peak_source": "live DFMA probe (hepmc_fp64_probe); MEASURED_PEAKS.json has no FP64 entry "
                                     "(hbm_gbs=%s)" % peaks.get("hbm_gbs"),
-                     "kernel_share_of_step": kernel_ms / (ms_total / steps)},
+                     "kernel_share_of_step": kernel_ms / (ms_total / steps),
+                     # the same launch read against HBM, to show which bound applies: the kernel has no
+                     # memory-resident input and writes one partial row (3 + ndim*K doubles) per chunk
+                     "hbm_view": {"bound": "hbm", "unit": "GB/s", "peak": peaks.get("hbm_gbs"),
+                                  "achieved": nc * (3 + NDIM * DIVISIONS) * 8 / (kernel_ms * 1e-3) / 1e9,
+                                  "bytes_per_launch": nc * (3 + NDIM * DIVISIONS) * 8},
+                     "note": "compute-bound FP64 SIMT kernel: 897 thread-instructions per point of which ~420 are the "
+                             "integer Philox4x32-10 rounds and 174 are FP64; issue slots 62 % busy (ncu, profiles/"
+                             "r01_vegas_sample_kernel_ncu_summary.txt)"},
         "cpu_baseline": cpu,
         "others": others,
     }
