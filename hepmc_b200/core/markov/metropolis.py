@@ -2,8 +2,8 @@
 
 `DefaultMetropolis(ndim, target, proposal=None)`: accept with min(1, pdf(cand)/pdf(state)).
 Device kernel: target = a built-in density (or its bound `pdf`), proposal =
-`proposals.Gaussian` with a diagonal covariance (random walk) or the reference's default
-`densities.Uniform` independence proposal.
+`proposals.Gaussian` with a diagonal covariance (random walk), `proposals.UniformLocal`, or
+the reference's default `densities.Uniform` independence proposal.
 """
 import numpy as np
 
@@ -36,8 +36,10 @@ class DefaultMetropolis(MetropolisUpdate):
         return self._proposal.proposal_pdf(state, candidate)
 
     def _proposal_params(self):
-        from ..proposals import Gaussian as GaussianProposal
+        from ..proposals import Gaussian as GaussianProposal, UniformLocal
         prop = self._proposal
+        if isinstance(prop, UniformLocal):
+            return 2, prop._kernel_params()
         if isinstance(prop, GaussianProposal):
             cov = np.asarray(prop.cov)
             if np.count_nonzero(cov - np.diag(np.diagonal(cov))):
@@ -45,7 +47,8 @@ class DefaultMetropolis(MetropolisUpdate):
             return 0, np.sqrt(np.diagonal(cov))
         if isinstance(prop, Uniform):
             return 1, np.array([prop.low, prop.high], dtype=np.float64)
-        raise TypeError("DefaultMetropolis on the device needs proposals.Gaussian or densities.Uniform, got "
+        raise TypeError("DefaultMetropolis on the device needs proposals.Gaussian, proposals.UniformLocal or "
+                        "densities.Uniform, got "
                         + type(prop).__name__)
 
     def _run_ensemble(self, x0, sample_size, thin, store_chain, first_chain, replay):

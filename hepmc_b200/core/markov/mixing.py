@@ -4,7 +4,8 @@
 the given probabilities.  Device kernel (`hepmc_mc3_chains`): the (MC)^3 combination the
 package is built around -- updates = [importance-sampling Metropolis whose proposal is a
 `MultiChannel`, local update], local update = `DefaultMetropolis` with a Gaussian proposal or
-`HamiltonianUpdate` (exact or ELM-surrogate gradient), all over one built-in target density.
+`proposals.UniformLocal`, or `HamiltonianUpdate` (exact or ELM-surrogate gradient), all over one
+built-in target density.
 """
 import ctypes
 
@@ -19,11 +20,11 @@ from . import ensemble
 
 
 def run_mc3(dens, channels, beta, local, x0, sample_size, thin, store_chain, first_chain, replay):
-    """Launch hepmc_mc3_chains.  `local` is None (beta == 1), a DefaultMetropolis with a Gaussian
-    proposal, or a HamiltonianUpdate."""
+    """Launch hepmc_mc3_chains.  `local` is None (beta == 1), a DefaultMetropolis with a Gaussian or
+    UniformLocal proposal, or a HamiltonianUpdate."""
     from ...hamiltonian.hmc import HamiltonianUpdate
     from ...surrogate.extreme_learning import SurrogateGradient
-    from ..proposals import Gaussian as GaussianProposal
+    from ..proposals import Gaussian as GaussianProposal, UniformLocal
     from ..densities import Gaussian as GaussianDensity
     dev = x0.device
     n_chains, ndim = x0.shape
@@ -51,9 +52,11 @@ def run_mc3(dens, channels, beta, local, x0, sample_size, thin, store_chain, fir
         if np.count_nonzero(cov - np.diag(np.diagonal(cov))):
             raise TypeError("the local random walk needs a diagonal proposal covariance")
         local_kind, scale = 0, np.diagonal(cov)
+    elif isinstance(local, DefaultMetropolis) and isinstance(local._proposal, UniformLocal):
+        local_kind, scale = 2, local._proposal._kernel_params()
     else:
-        raise TypeError("the local update must be HamiltonianUpdate or DefaultMetropolis(proposals.Gaussian), got "
-                        + type(local).__name__)
+        raise TypeError("the local update must be HamiltonianUpdate or DefaultMetropolis with proposals.Gaussian / "
+                        "proposals.UniformLocal, got " + type(local).__name__)
     sel = draw = u = None
     if replay is not None:
         sel, _ = _lib.to_device(replay[0], dtype=torch.int64)

@@ -1,4 +1,5 @@
 """Proposal generators understood by the chain kernels."""
 from .gaussian import Gaussian
+from .uniform_local import UniformLocal
 
-__all__ = ["Gaussian"]
+__all__ = ["Gaussian", "UniformLocal"]

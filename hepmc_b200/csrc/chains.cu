@@ -50,10 +50,20 @@ __global__ void __launch_bounds__(128) rwm_kernel(const __grid_constant__ Dens d
                     if (2 * k + 1 < NDIM) z[(2 * k + 1) % NDIM] = z1;
                 }
             }
+            if (a.prop_kind == 2) {
+                // proposals/uniform_local.py:27-29: a box of edge delta around the state, pushed back
+                // into [lo, hi]; ONE uniform per step moves every coordinate (np.random.rand() is scalar)
 #pragma unroll
-            for (int d = 0; d < NDIM; ++d)
-                cand[d] = a.prop_kind == 0 ? x[d] + a.scale[d] * z[d]            // proposals/gaussian.py:25-27
-                                           : a.prop_lo + (a.prop_hi - a.prop_lo) * z[d];  // uniform.py:33-34
+                for (int d = 0; d < NDIM; ++d) {
+                    const double base = fmax(a.prop_lo, x[d] - a.scale[d] / 2);
+                    cand[d] = fmin(base, a.prop_hi - a.scale[d]) + z[0] * a.scale[d];
+                }
+            } else {
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d)
+                    cand[d] = a.prop_kind == 0 ? x[d] + a.scale[d] * z[d]            // proposals/gaussian.py:25-27
+                                               : a.prop_lo + (a.prop_hi - a.prop_lo) * z[d];  // uniform.py:33-34
+            }
             const double cpdf = density_pdf_n<NDIM>(dens, cand);
             const double ratio = cpdf / pdf;  // metropolis.py:50
             double u;
@@ -220,11 +230,14 @@ int hepmc_rwm_chains(const hepmc_density_t* dens, const double* x0_dev, int prop
                             sample_size, thin, seed, stream_id, z_replay_dev, u_replay_dev, chain_dev, last_dev,
                             accepted_dev, total_accepted_dev);
     if (e) return e;
-    HEPMC_REQUIRE(proposal_kind == 0 || proposal_kind == 1, HEPMC_E_ARG, "hepmc_rwm_chains: proposal_kind must be 0 or 1");
+    HEPMC_REQUIRE(proposal_kind >= 0 && proposal_kind <= 2, HEPMC_E_ARG, "hepmc_rwm_chains: proposal_kind must be 0, 1 or 2");
     a.prop_kind = proposal_kind;
     if (proposal_kind == 1) {
         a.prop_lo = prop_scale_host[0];
         a.prop_hi = prop_scale_host[1];
+    } else if (proposal_kind == 2) {
+        a.prop_lo = prop_scale_host[dens->ndim];
+        a.prop_hi = prop_scale_host[dens->ndim + 1];
     }
     if (n_chains == 0) return 0;
     const int threads = 128;

@@ -18,7 +18,7 @@ struct ChainArgs {
     int64_t* accepted;       // (C,)
     unsigned long long* total_accepted;
     double scale[HEPMC_MAX_CHAIN_DIM];  // rwm: sqrt(diag cov); hmc: sqrt(mass)
-    int prop_kind;                      // rwm: 0 = Gaussian random walk, 1 = uniform independence on (lo, hi)
+    int prop_kind;                      // rwm: 0 = Gaussian random walk, 1 = uniform independence on (lo, hi), 2 = UniformLocal (scale = delta, box [lo, hi])
     double prop_lo, prop_hi;
     // hmc
     double step_size;

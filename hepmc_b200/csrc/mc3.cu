@@ -15,7 +15,8 @@ struct Mc3Args {
     const double* table;  // (nch, kMcRow) channel table, see hepmc_multichannel_sample
     int nch;
     double beta;          // probability of the importance-sampling update
-    int local_kind;       // 0 = Gaussian random walk (scale = sqrt(diag cov)), 1 = HMC (scale = sqrt(mass))
+    int local_kind;       // 0 = Gaussian random walk (scale = sqrt(diag cov)), 1 = HMC (scale = sqrt(mass)),
+                          // 2 = UniformLocal (scale = delta, box [prop_lo, prop_hi])
     const int64_t* sel_replay;  // (C, T-1): 0 = IS update, 1 = local update
 };
 
@@ -137,6 +138,22 @@ __global__ void __launch_bounds__(128) mc3_kernel(const __grid_constant__ Dens d
                 for (int d = 0; d < NDIM; ++d) cand[d] = x[d] + a.scale[d] * z[d];
                 cpdf = density_pdf_n<NDIM>(dens, cand);
                 prob = cpdf / pdf;  // metropolis.py:50
+            } else if (m.local_kind == 2) {
+                // ---- local UniformLocal Metropolis (proposals/uniform_local.py:27-29; one uniform per step)
+                double u0;
+                if (replay) {
+                    u0 = draw[0];
+                } else {
+                    const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), base + 1u, a.stream_id, key);
+                    u0 = u52(r.x, r.y);
+                }
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) {
+                    const double lo = fmax(a.prop_lo, x[d] - a.scale[d] / 2);
+                    cand[d] = fmin(lo, a.prop_hi - a.scale[d]) + u0 * a.scale[d];
+                }
+                cpdf = density_pdf_n<NDIM>(dens, cand);
+                prob = cpdf / pdf;  // metropolis.py:50 (the reference treats the proposal as symmetric)
             } else {
                 // ---- local HMC (hmc.py:54-88, simulation.py:34-42)
                 double p0[NDIM], p[NDIM], grad[NDIM];
@@ -218,7 +235,7 @@ extern "C" int hepmc_mc3_chains(const hepmc_density_t* dens, const double* chann
                   HEPMC_MAX_CHAIN_DIM);
     HEPMC_REQUIRE(n_channels >= 1 && n_channels <= HEPMC_MAX_CHANNELS, HEPMC_E_UNSUPPORTED, "hepmc_mc3_chains: bad channel count");
     HEPMC_REQUIRE(beta >= 0.0 && beta <= 1.0, HEPMC_E_ARG, "hepmc_mc3_chains: beta outside [0,1]");
-    HEPMC_REQUIRE(local_kind == 0 || local_kind == 1, HEPMC_E_ARG, "hepmc_mc3_chains: local_kind must be 0 or 1");
+    HEPMC_REQUIRE(local_kind >= 0 && local_kind <= 2, HEPMC_E_ARG, "hepmc_mc3_chains: local_kind must be 0, 1 or 2");
     HEPMC_REQUIRE(beta >= 1.0 || local_scale_host, HEPMC_E_ARG, "hepmc_mc3_chains: local update parameters missing");
     HEPMC_REQUIRE(precision == 0 || precision == 1, HEPMC_E_UNSUPPORTED, "hepmc_mc3_chains: precision must be 0 or 1");
     HEPMC_REQUIRE(n_chains >= 0 && first_chain >= 0 && sample_size >= 1 && thin >= 1 && steps >= 0, HEPMC_E_ARG,
@@ -239,9 +256,14 @@ extern "C" int hepmc_mc3_chains(const hepmc_density_t* dens, const double* chann
     for (int d = 0; d < nd; ++d) {
         const double v = local_scale_host ? local_scale_host[d] : 1.0;  // diag cov (random walk) or mass (HMC)
         HEPMC_REQUIRE(v > 0.0, HEPMC_E_ARG, "hepmc_mc3_chains: local covariance / mass must be positive");
-        a.scale[d] = sqrt(v);
+        a.scale[d] = local_kind == 2 ? v : sqrt(v);   // UniformLocal: delta itself
         pd.a[d] = 0.0; pd.b[d] = sqrt(1.0 / v); pd.c[d] = 1.0 / v;
         logdet += log(v);
+    }
+    if (local_kind == 2) {
+        HEPMC_REQUIRE(local_scale_host != nullptr, HEPMC_E_ARG, "hepmc_mc3_chains: UniformLocal needs delta and its range");
+        a.prop_lo = local_scale_host[nd];
+        a.prop_hi = local_scale_host[nd + 1];
     }
     pd.s1 = nd * log(2.0 * 3.141592653589793) + logdet;
     hepmc_elm_t el{};

@@ -7,6 +7,7 @@ import numpy as np
 
 from ..core.densities import Gaussian
 from ..core.markov import MixingMarkovUpdate, DefaultMetropolis
+from ..core.proposals import UniformLocal
 from ..core.integration import MultiChannelMC
 from ..hamiltonian import HamiltonianUpdate
 
@@ -60,6 +61,17 @@ def _forward(owner, name):
     """Property forwarding attribute `name` to the sub-object `owner` (e.g. the local sampler)."""
     return property(lambda self: getattr(getattr(self, owner), name),
                     lambda self, value: setattr(getattr(self, owner), name, value))
+
+
+class MC3Uniform(BasicMC3):
+    """(MC)^3 with a local uniform-box Metropolis update of edge `delta` (mc3.py:100-114)."""
+
+    delta = _forward("_local_proposal", "delta")
+
+    def __init__(self, fn, channels, delta, beta=.5):
+        self._local_proposal = UniformLocal(channels.ndim, delta)
+        BasicMC3.__init__(self, fn, channels,
+                          DefaultMetropolis(channels.ndim, fn, self._local_proposal), beta)
 
 
 class MC3Hamilton(BasicMC3):

@@ -230,7 +230,10 @@ int hepmc_accept_flags(const double* f_dev, const double* q_dev, double q_scalar
 /* x0_dev (n_chains, ndim).  proposal_kind 0: Gaussian random walk, prop_scale_host[ndim] =
  * sqrt(diag(cov)); proposal_kind 1: independence proposal uniform on (prop_scale_host[0],
  * prop_scale_host[1])^ndim = DefaultMetropolis' default Uniform(ndim) (metropolis.py:114-115,
- * uniform.py:33-34; the replay tape then holds uniforms).  sample_size T >= 1
+ * uniform.py:33-34; the replay tape then holds uniforms); proposal_kind 2: UniformLocal
+ * (proposals/uniform_local.py:5-50), prop_scale_host = [delta_0 .. delta_{ndim-1}, low, high]:
+ * candidate_d = min(max(low, x_d - delta_d/2), high - delta_d) + u delta_d with ONE uniform u per
+ * step (column 0 of the replay tape), plain Metropolis ratio.  sample_size T >= 1
  * (chain[0] = x0, T-1 transitions).  Chain c has global index first_chain + c.
  * Replay tapes: z_replay_dev (n_chains, T-1, ndim), u_replay_dev (n_chains, T-1).
  * Outputs: chain_dev (n_chains, n_kept, ndim) with n_kept = ceil(T / thin), storing states
@@ -283,11 +286,13 @@ int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int pr
  * (candidate drawn from the channel mixture, Hastings ratio pdf(c) q(x) / (pdf(x) q(c)),
  * metropolis.py:46-47), otherwise the local update: local_kind 0 = Gaussian random walk with
  * diag covariance local_scale_host[ndim]; local_kind 1 = HMC with diag mass local_scale_host[ndim],
- * step_size, steps and the exact or ELM-surrogate gradient (elm may be NULL; precision 0/1).
+ * step_size, steps and the exact or ELM-surrogate gradient (elm may be NULL; precision 0/1);
+ * local_kind 2 = UniformLocal Metropolis (mc3.MC3Uniform, mc3.py:100-114), local_scale_host =
+ * [delta_0 .. delta_{ndim-1}, low, high] as in hepmc_rwm_chains (uniform in column 0 of the draw tape).
  * channel_table_dev as in hepmc_multichannel_sample.  Replay tapes (all three or none):
  * sel_replay_dev (C, T-1) int64 (0 = IS update, 1 = local), draw_replay_dev (C, T-1, ndim) = the
- * candidate (IS) / standard normals (random walk) / momentum (HMC), u_replay_dev (C, T-1).
- * Outputs as hepmc_rwm_chains. */
+ * candidate (IS) / standard normals (random walk) / momentum (HMC) / proposal uniform (UniformLocal),
+ * u_replay_dev (C, T-1).  Outputs as hepmc_rwm_chains. */
 int hepmc_mc3_chains(const hepmc_density_t* dens, const double* channel_table_dev, int n_channels, double beta,
                      int local_kind, const double* local_scale_host, double step_size, int steps,
                      const hepmc_elm_t* elm, int precision, const double* x0_dev,

@@ -331,6 +331,39 @@ def gen_metropolis(h):
     out["gauss_z"] = np.stack(zs)
     out["gauss_u"] = u
     out["gauss_cov"] = np.array([0.5, 0.5, 0.5])
+    # camel-2D target, UniformLocal proposal (proposals/uniform_local.py): per step the proposal's
+    # scalar uniform, then (if the ratio is below one) the accept uniform
+    x0s = [np.array([0.3, 0.35]), np.array([0.95, 0.02])]
+    delta = np.array([0.2, 0.3])
+    chains, accs, vs, us = [], [], [], []
+    for x0 in x0s:
+        upd = h.DefaultMetropolis(2, h.densities.Camel(2), h.proposals.UniformLocal(2, delta))
+        with Tape() as t:
+            marks = []
+            orig_next = upd.next_state
+
+            def next_state(state, it, _o=orig_next, _m=marks, _t=t):
+                before = len(_t.log["rand"])
+                out_state = _o(state, it)
+                _m.append(len(_t.log["rand"]) - before)
+                return out_state
+            upd.next_state = next_state
+            smp = upd.sample(T, x0, log_every=-1)
+        flat = [float(v) for v in t.log["rand"]]
+        v, u, k = np.empty(T - 1), np.full(T - 1, np.nan), 0
+        for i, m in enumerate(marks):
+            assert m in (1, 2)
+            v[i] = flat[k]
+            if m == 2:
+                u[i] = flat[k + 1]
+            k += m
+        chains.append(smp.data); accs.append(smp.accepted); vs.append(v); us.append(u)
+    out["ulocal_x0"] = np.stack(x0s)
+    out["ulocal_chain"] = np.stack(chains)
+    out["ulocal_accepted"] = np.array(accs, dtype=np.int64)
+    out["ulocal_v"] = np.stack(vs)
+    out["ulocal_u"] = np.stack(us)
+    out["ulocal_delta"] = delta
     save("metropolis", **out)
 
 
@@ -521,8 +554,8 @@ def gen_mixing(h):
     D = h.densities
     T = 300
     weights = np.array([0.4, 0.4, 0.2])
-    for tag in ("hmc", "rwm"):
-        np.random.seed(SEED + (1 if tag == "rwm" else 0))
+    for tag in ("hmc", "rwm", "unif"):
+        np.random.seed(SEED + {"hmc": 0, "rwm": 1, "unif": 2}[tag])
         target = D.Camel(2)
         channels = h.MultiChannel([D.Gaussian(2, mu=1 / 3, scale=0.1), D.Gaussian(2, mu=2 / 3, scale=0.1), D.Uniform(2)],
                                   weights.copy())
@@ -530,9 +563,12 @@ def gen_mixing(h):
         if tag == "hmc":
             local = h.hamiltonian.HamiltonianUpdate(target, D.Gaussian(2, cov=1.), 10, 0.02)
             local_var = np.array([1., 1.])
-        else:
+        elif tag == "rwm":
             local = h.DefaultMetropolis(2, target, h.proposals.Gaussian(2, cov=np.diag([0.002, 0.003])))
             local_var = np.array([0.002, 0.003])
+        else:   # MC3Uniform's local update (mc3.py:100-106); local_var holds delta
+            local = h.DefaultMetropolis(2, target, h.proposals.UniformLocal(2, np.array([0.2, 0.3])))
+            local_var = np.array([0.2, 0.3])
         mix = h.MixingMarkovUpdate(2, [is_upd, local], [0.4, 0.6])
         x0s = [np.array([0.3, 0.35]), np.array([0.7, 0.6])]
         chains, accs, sels, draws, us = [], [], [], [], []
@@ -561,13 +597,16 @@ def gen_mixing(h):
                     nz, nu = len(tp.log["z"]), len(tp.log["rand"])
                     out_state = _o(state, it)
                     sel = log["sel"][-1]
+                    nunif = len(tp.log["rand"]) - nu
                     if sel == 0:
                         dr = log["cand"]
                     elif tag == "hmc":
                         dr = log["p"]
-                    else:
+                    elif tag == "rwm":
                         dr = np.ravel(tp.log["z"][-1])
-                    nunif = len(tp.log["rand"]) - nu
+                    else:   # the proposal's scalar np.random.rand() comes first, then the accept uniform
+                        dr = np.array([float(tp.log["rand"][nu]), np.nan])
+                        nunif -= 1
                     assert nunif in (0, 1)
                     steps_log.append((sel, np.array(dr, copy=True), float(tp.log["rand"][-1]) if nunif else np.nan))
                     return out_state

@@ -445,6 +445,36 @@ def test_metropolis_replay(tag):
         met.sample(10, np.zeros(ndim + 1))
 
 
+def test_uniform_local_metropolis():
+    """proposals.UniformLocal (the local update of MC3Uniform): replay of the reference's draws,
+    native draws against the oracle, parameter checks."""
+    g = G("metropolis")
+    delta = g["ulocal_delta"]
+    met = H.DefaultMetropolis(2, H.densities.Camel(2), H.proposals.UniformLocal(2, delta))
+    assert not met.is_hasting
+    T = g["ulocal_chain"].shape[1]
+    v = np.repeat(g["ulocal_v"][:, :, None], 2, axis=2)     # tape layout (C, T-1, ndim); column 0 is read
+    s = met.sample(T, g["ulocal_x0"], replay=(v, _fill(g["ulocal_u"])))
+    assert np.array_equal(s.accepted, g["ulocal_accepted"])
+    assert_close(s.data, g["ulocal_chain"], RTOL)
+    H.seed(77)
+    C, T = 256, 100
+    x0 = np.tile([0.9, 0.05], (C, 1))
+    s = met.sample(T, x0, first_chain=7)
+    w = O.philox_words(77, 0, 7 + np.arange(C), 2 * (T - 1)).astype(np.uint32)
+    vv = O.u52(w[:, 0::2, 0], w[:, 0::2, 1])
+    uu = O.u52(w[:, 1::2, 0], w[:, 1::2, 1])
+    chain, acc = O.uniform_local_chains(O.camel_pdf, x0, vv, uu, delta)
+    assert np.array_equal(s.accepted, acc)
+    assert_close(s.data, chain, 1e-12, atol=1e-15)
+    assert s.data.min() >= 0.0 and s.data.max() <= 1.0       # the box is pushed back into [0, 1]
+    with pytest.raises(ValueError):
+        H.proposals.UniformLocal(2, 1.5)
+    with pytest.raises(ValueError):
+        H.proposals.UniformLocal(2, [0.1, 0.2, 0.3])
+    assert H.proposals.UniformLocal(3, 0.1).proposal_pdf(None, None) == pytest.approx(1e3)
+
+
 def test_metropolis_native_matches_oracle_draws():
     H.seed(31337)
     C, T, ndim = 64, 200, 2
@@ -513,12 +543,14 @@ def _mixing_setup(tag, weights):
     is_upd = H.DefaultMetropolis(2, target, channels)
     if tag == "hmc":
         local = H.hamiltonian.HamiltonianUpdate(target, H.densities.Gaussian(2, cov=1.), 10, 0.02)
-    else:
+    elif tag == "rwm":
         local = H.DefaultMetropolis(2, target, H.proposals.Gaussian(2, cov=np.diag([0.002, 0.003])))
+    else:
+        local = H.DefaultMetropolis(2, target, H.proposals.UniformLocal(2, np.array([0.2, 0.3])))
     return target, channels, is_upd, local
 
 
-@pytest.mark.parametrize("tag", ["hmc", "rwm"])
+@pytest.mark.parametrize("tag", ["hmc", "rwm", "unif"])
 def test_mixing_replay(tag):
     g = G("mixing")
     target, channels, is_upd, local = _mixing_setup(tag, g["weights"])
@@ -559,6 +591,21 @@ def test_mixing_native_and_mc3():
     assert mc3.channels.channels_weight[2] < 0.25
     res = mc3.sample(50)
     assert res.data.shape == (50, 2)
+    # MC3Uniform (mc3.py:100-114): the same with the local uniform-box update
+    H.seed(407)
+    mc3u = H.mc3.MC3Uniform(H.densities.Camel(2), H.MultiChannel([H.densities.Gaussian(2, mu=1 / 3, scale=0.1),
+                            H.densities.Gaussian(2, mu=2 / 3, scale=0.1), H.densities.Uniform(2)]), 0.1, beta=0.5)
+    assert np.allclose(mc3u.delta, 0.1)
+    mc3u.delta = 0.15
+    assert np.allclose(mc3u.sample_local._proposal.delta, 0.15)
+    mc3u.integrate([], [2000] * 5, [])
+    s = mc3u.mixing_sampler.sample(T, x0, store_chain=False)
+    # no KS gate here: the reference's UniformLocal moves all coordinates with one uniform and is
+    # treated as symmetric although the box is shifted at the borders, so the local update alone is
+    # neither ergodic nor exactly reversible; the mixed chain is close to, not exactly, the target
+    pts = s.data[:, 0]
+    assert abs(pts.mean() - 0.5) < 0.02 and abs(pts.var(axis=0).mean() / 0.0328 - 1) < 0.15
+    assert 0.2 < s.accepted.mean() / T < 0.95
 
 
 # ------------------------------------------------------------------ ELM + HMC

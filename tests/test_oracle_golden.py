@@ -181,7 +181,7 @@ def test_multichannel():
     assert_close(O.multichannel_pdf(chans, [0.2, 0.5, 0.3], g["pdf_xs"]), g["pdf"], 1e-14)
 
 
-@pytest.mark.parametrize("tag,kind", [("hmc", 1), ("rwm", 0)])
+@pytest.mark.parametrize("tag,kind", [("hmc", 1), ("rwm", 0), ("unif", 2)])
 def test_mixing_chains(tag, kind):
     g = G("mixing")
     chans = [("gauss", 1 / 3, 0.01), ("gauss", 2 / 3, 0.01), ("uniform", 0., 1.)]
@@ -190,6 +190,14 @@ def test_mixing_chains(tag, kind):
                                  pot_grad_fn=O.camel_pot_gradient, step_size=0.02, steps=10)
     assert np.array_equal(acc, g[tag + "_accepted"])
     assert_close(chain, g[tag + "_chain"], 1e-10, atol=1e-12)
+
+
+def test_uniform_local_chains():
+    """DefaultMetropolis + proposals.UniformLocal (uniform_local.py:27-29), one start in a corner."""
+    g = G("metropolis")
+    chain, acc = O.uniform_local_chains(O.camel_pdf, g["ulocal_x0"], g["ulocal_v"], _fill(g["ulocal_u"]), g["ulocal_delta"])
+    assert np.array_equal(acc, g["ulocal_accepted"])
+    assert np.array_equal(chain, g["ulocal_chain"])
 
 
 @pytest.mark.parametrize("n,e_cm", [(3, 50.), (4, 100.), (6, 1000.)])
