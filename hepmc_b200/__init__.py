@@ -24,5 +24,6 @@ from .core.density import Proposal, Density, Distribution
 from . import hamiltonian
 from . import surrogate
 from . import mc3
+from . import interfaces
 
 __version__ = "0.1.0"

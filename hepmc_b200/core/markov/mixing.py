@@ -98,10 +98,17 @@ class MixingMarkovUpdate(MarkovUpdate):
         if self.updates_count != 2:
             raise TypeError("the device kernel mixes exactly [importance-sampling Metropolis, local update]")
         is_upd, local = self.updates
-        if not (isinstance(is_upd, DefaultMetropolis) and isinstance(is_upd._proposal, MultiChannel)):
-            raise TypeError("updates[0] must be DefaultMetropolis(ndim, target, MultiChannel(...))")
+        from ..densities import Uniform
+        if isinstance(is_upd, DefaultMetropolis) and isinstance(is_upd._proposal, Uniform):
+            # the reference's default independence proposal (interfaces/mc3_hmc_uni.py:14) is the
+            # one-channel mixture: constant q, the Hastings ratio reduces to the plain one
+            channels = MultiChannel([is_upd._proposal])
+        elif isinstance(is_upd, DefaultMetropolis) and isinstance(is_upd._proposal, MultiChannel):
+            channels = is_upd._proposal
+        else:
+            raise TypeError("updates[0] must be DefaultMetropolis(ndim, target[, MultiChannel(...)])")
         dens = as_builtin(is_upd.target) or as_builtin(is_upd.pdf)
         if dens is None:
             raise TypeError("the mixed updates need a built-in target density; there is no CPU fallback")
-        return run_mc3(dens, is_upd._proposal, float(self.weights[0]), local, x0, sample_size, thin, store_chain,
+        return run_mc3(dens, channels, float(self.weights[0]), local, x0, sample_size, thin, store_chain,
                        first_chain, replay)

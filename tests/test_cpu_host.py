@@ -143,3 +143,45 @@ def test_rng_streams():
     assert H.rng.get_seed() == 7 and H.rng.next_stream() == 0 and H.rng.next_stream(10) == 1
     assert H.rng.next_stream() == 11
     H.seed(1234)
+
+
+def test_stat_tools_host_logic_matches_numpy():
+    """Bin edges and percentiles prepared on the host for the statistics kernels are NumPy's
+    (np.histogramdd / np.percentile 'linear'), checked on CPU tensors."""
+    import torch
+    from hepmc_b200.core.util import stat_tools
+    rs = np.random.RandomState(3)
+    data = rs.randn(501, 3) * [1., 0.1, 7.]
+    x = torch.from_numpy(data)
+    for bins, rng_ in ((7, None), ((3, 4, 5), None), (6, ((-1, 1), (-0.5, 2), (0, 0.3))),
+                       ((np.array([-1., 0., 0.5, 3.]), 5, 2), None)):
+        edges = stat_tools._edges(x, bins, rng_)
+        ref = np.histogramdd(data, bins, rng_)[1]
+        assert len(edges) == 3 and all(np.array_equal(e, r) for e, r in zip(edges, ref))
+    flat = torch.from_numpy(np.full((5, 2), 0.25))
+    assert all(np.array_equal(e, r) for e, r in zip(stat_tools._edges(flat, 4, None),
+                                                   np.histogramdd(np.full((5, 2), 0.25), 4)[1]))
+    with pytest.raises(ValueError):
+        stat_tools._edges(x, (3, 4), None)
+    with pytest.raises(ValueError):
+        stat_tools._edges(x, 0, None)
+    srt = torch.sort(x, dim=0).values
+    for q in (0.25, 0.5, 0.75, 0.0, 1.0, 0.333):
+        for d in range(3):
+            assert stat_tools._percentile(srt[:, d], q) == np.percentile(data[:, d], 100 * q)
+
+
+def test_interfaces_namespace():
+    """Recipe names and signatures of hepmc/interfaces/*.py; NUTS recipes are declared out of scope."""
+    import inspect
+    import hepmc_b200 as H
+    names = ["plain_uniform", "plain_hmc", "plain_nuts", "plain_spherical_nuts", "mc3_gauss", "mc3_hmc",
+             "mc3_nuts", "mc3_spherical_nuts", "mc3_hmc_el", "mc3_nuts_el", "mc3_spherical_nuts_el", "mc3_hmc_uni"]
+    assert sorted(names) == H.interfaces.__all__
+    sig = inspect.signature(H.interfaces.mc3_hmc_el.get_sampler)
+    assert list(sig.parameters) == ["target", "ndim", "initial", "centers", "widths", "beta", "nintegral", "mass",
+                                    "steps", "step_size", "el_size"]
+    assert sig.parameters["el_size"].default == 100 and sig.parameters["mass"].default == 10
+    assert list(inspect.signature(H.interfaces.mc3_gauss.get_sampler).parameters)[-1] == "local_width"
+    with pytest.raises(NotImplementedError):
+        H.interfaces.plain_nuts.get_sampler(None, 2, 0.5)

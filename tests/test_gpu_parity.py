@@ -926,3 +926,40 @@ def test_bin_wise_chi2_vs_reference():
     # nothing qualifies -> (None, None, None) like the reference
     assert stat_tools.bin_wise_chi2(H.core.sampling.Sample(data=g["camel_data"][:50], target=H.densities.Camel(2)),
                                     bins=40) == (None, None, None)
+
+
+# ------------------------------------------------------------------ interfaces recipes (hepmc/interfaces/*.py)
+def test_interfaces_recipes():
+    """get_sampler(...) with the reference's argument lists; every returned sampler runs in the
+    chain kernels and samples the 2-D camel (moments; KS for the exact-gradient recipes)."""
+    from oracle.stats_oracle import ks
+    gh = G("camel2d_reference_hist")
+    centers, widths = [1 / 3, 2 / 3], [0.1, 0.1]
+    C, T = 4000, 150
+    recipes = (
+        ("plain_uniform", (), {}),
+        ("plain_hmc", (), dict(mass=1., steps=10, step_size=0.02)),
+        ("mc3_gauss", (centers, widths, 0.5), dict(nintegral=4000, local_width=0.05)),
+        ("mc3_hmc", (centers, widths, 0.5), dict(nintegral=4000, mass=1., steps=10, step_size=0.02)),
+        ("mc3_hmc_uni", (0.5,), dict(mass=1., steps=10, step_size=0.02)),
+        ("mc3_hmc_el", (centers, widths, 0.5), dict(nintegral=4000, mass=1., steps=10, step_size=0.02, el_size=100)),
+    )
+    for k, (name, args, kw) in enumerate(recipes):
+        H.seed(900 + k)
+        target = H.densities.Camel(2)
+        sampler, initial = getattr(H.interfaces, name).get_sampler(target, 2, 0.4, *args, **kw)
+        assert np.array_equal(initial, np.full(2, 0.4))
+        one = sampler.sample(50, initial)                     # the reference's single-chain call
+        assert one.data.shape == (50, 2)
+        x0 = np.tile([0.35, 0.3], (C, 1))
+        x0[C // 2:] = [0.65, 0.7]
+        s = sampler.sample(T, x0, store_chain=False)
+        pts = s.data[:, 0]
+        assert abs(pts.mean() - 0.5) < 0.02, name
+        assert abs(pts.var(axis=0).mean() / 0.0328 - 1) < 0.15, name
+        if name in ("mc3_gauss", "mc3_hmc", "mc3_hmc_uni", "mc3_hmc_el"):
+            hist, _ = np.histogramdd(pts, bins=[gh["edges"][0], gh["edges"][1]])
+            res = np.array(ks(hist, gh["truth"]))
+            assert np.all(res[:, 0] < 1.5 * res[:, 1]), (name, res)   # 8 KS checks at alpha = 0.05: some slack
+    with pytest.raises(NotImplementedError):
+        H.interfaces.mc3_nuts.get_sampler(H.densities.Camel(2), 2, 0.4, centers, widths, 0.5)
