@@ -18,6 +18,11 @@ from .simulation import HamiltonLeapfrog
 from .. import _lib
 
 
+# cancellation ratio of the surrogate gradient above which precision='tc' warns (measured:
+# <= ~300 is harmless, ~1e4 halves the acceptance rate; scripts/tc_conditioning.py)
+TC_CANCELLATION_LIMIT = 2000.0
+
+
 class HamiltonianUpdate(MetropolisUpdate):
 
     def __init__(self, target_density, p_dist, steps, step_size, simulate=None,
@@ -75,6 +80,16 @@ class HamiltonianUpdate(MetropolisUpdate):
         prec = {"f64": 0, "f32": 1, "tc": 2}[self.precision]
         if elm_blk is None:
             prec = 0
+        if prec == 2 and not getattr(self, "_tc_checked", False):
+            # one-time guard: TF32 operands cannot resolve a heavily cancelling weight vector
+            self._tc_checked = True
+            kappa = grad.cancellation(x0[:256])
+            if kappa > TC_CANCELLATION_LIMIT:
+                import warnings
+                warnings.warn("precision='tc': the surrogate's gradient sum cancels by a factor %.0f (> %.0f); TF32 "
+                              "operands lose it and the acceptance rate will drop (the sampler stays exact).  Retrain "
+                              "with extreme_learning_train(..., ridge=1e-6) or use precision='f32'."
+                              % (kappa, TC_CANCELLATION_LIMIT), RuntimeWarning, stacklevel=3)
         out = ensemble.run_hmc(tgt._block(), elm_blk, prec, x0, mass, self.step_size, self.steps,
                                sample_size, thin, store_chain, first_chain, None, replay)
         del keep
