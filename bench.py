@@ -389,7 +389,7 @@ def other_workloads(H, _lib, torch, fp64_peak, with_cpu, rank=0, world=1):
         basis = H.surrogate.GaussianBasis(8)
         params = (rs.random((nodes, 8)), 0.01 + 0.99 * rs.random(nodes), None)
         w = 0.01 * rs.standard_normal(nodes)
-        for prec in ("f64", "f32", "tc"):
+        for prec in ("f64", "f32", "tc32", "tc"):
             tgt = H.densities.Camel(8)
             H.surrogate.attach_surrogate_gradient(tgt, basis, params, 0.0, w)
             upd = H.hamiltonian.HamiltonianUpdate(tgt, H.densities.Gaussian(8), 20, 0.01, precision=prec)

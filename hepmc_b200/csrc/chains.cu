@@ -261,7 +261,7 @@ int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int pr
     HEPMC_REQUIRE(dens->kind >= HEPMC_CAMEL && dens->kind <= HEPMC_UNIFORM, HEPMC_E_ARG,
                   "hepmc_hmc_chains: target must be a built-in density (kind %d)", dens->kind);
     HEPMC_REQUIRE(steps >= 0, HEPMC_E_ARG, "hepmc_hmc_chains: steps < 0");
-    HEPMC_REQUIRE(precision >= 0 && precision <= 2, HEPMC_E_ARG, "hepmc_hmc_chains: precision must be 0, 1 or 2");
+    HEPMC_REQUIRE(precision >= 0 && precision <= 3, HEPMC_E_ARG, "hepmc_hmc_chains: precision must be 0, 1, 2 or 3");
     const int nd = dens->ndim;
     ChainArgs a{};
     int e = fill_chain_args(a, "hepmc_hmc_chains", nd, x0_dev, mass_host, nd, true, n_chains, first_chain, sample_size, thin,
@@ -293,12 +293,12 @@ int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int pr
     pd.s1 = nd * log(2.0 * 3.141592653589793) + logdet;
     if (n_chains == 0) return 0;
     cudaStream_t st = as_stream(stream);
-    if (precision == 2 && el.mode != HEPMC_GRAD_EXACT) {
+    if (precision >= 2 && el.mode != HEPMC_GRAD_EXACT) {
         HEPMC_REQUIRE(el.mode == HEPMC_GRAD_ELM_GAUSS, HEPMC_E_UNSUPPORTED,
                       "hepmc_hmc_chains: the tensor-core path implements the Gaussian basis");
-        return launch_hmc_tc(*dens, pd, el, a, st);
+        return launch_hmc_tc(*dens, pd, el, a, precision == 3, st);
     }
-    if (precision == 2) precision = 0;  // exact gradient: nothing to put on tensor cores
+    if (precision >= 2) precision = 0;  // exact gradient: nothing to put on tensor cores
     const int threads = 128;
     const unsigned blocks = (unsigned)((n_chains + threads - 1) / threads);
     int dev = 0, maxs = 0;

@@ -52,7 +52,9 @@ __device__ __forceinline__ void finish_counts(const ChainArgs& a, bool active, i
 
 
 // tensor-core launchers (elm_tc.cu)
-int launch_hmc_tc(const Dens& dens, const Dens& pdist, const hepmc_elm_t& elm, const ChainArgs& a, cudaStream_t st);
-int launch_elm_grad_tc(const hepmc_elm_t& elm, int ndim, const double* xs, int64_t n, double* out, cudaStream_t st);
+int launch_hmc_tc(const Dens& dens, const Dens& pdist, const hepmc_elm_t& elm, const ChainArgs& a, bool fma_g2,
+                  cudaStream_t st);
+int launch_elm_grad_tc(const hepmc_elm_t& elm, int ndim, const double* xs, int64_t n, double* out, bool fma_g2,
+                       cudaStream_t st);
 
 }  // namespace hepmc

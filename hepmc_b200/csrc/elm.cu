@@ -66,13 +66,13 @@ extern "C" int hepmc_elm_eval(const hepmc_elm_t* elm, int ndim, int what, int pr
     HEPMC_REQUIRE(elm->nodes >= 1 && elm->p0_dev && elm->p1_dev, HEPMC_E_ARG, "hepmc_elm_eval: incomplete parameters");
     HEPMC_REQUIRE(what >= 0 && what <= 2, HEPMC_E_ARG, "hepmc_elm_eval: what must be 0, 1 or 2");
     HEPMC_REQUIRE(what == 2 || elm->out_w_dev, HEPMC_E_ARG, "hepmc_elm_eval: out_w_dev is NULL");
-    HEPMC_REQUIRE(precision >= 0 && precision <= 2, HEPMC_E_ARG, "hepmc_elm_eval: precision must be 0, 1 or 2");
-    if (precision == 2) {
+    HEPMC_REQUIRE(precision >= 0 && precision <= 3, HEPMC_E_ARG, "hepmc_elm_eval: precision must be 0, 1, 2 or 3");
+    if (precision >= 2) {
         HEPMC_REQUIRE(what == 1 && elm->mode == HEPMC_GRAD_ELM_GAUSS, HEPMC_E_UNSUPPORTED,
                       "hepmc_elm_eval: the tensor-core path implements eval_gradient of the Gaussian basis");
         if (n == 0) return 0;
         HEPMC_REQUIRE(xs_dev && out_dev, HEPMC_E_ARG, "hepmc_elm_eval: NULL buffer");
-        return launch_elm_grad_tc(*elm, ndim, xs_dev, n, out_dev, as_stream(stream));
+        return launch_elm_grad_tc(*elm, ndim, xs_dev, n, out_dev, precision == 3, as_stream(stream));
     }
     HEPMC_REQUIRE(n >= 0, HEPMC_E_ARG, "hepmc_elm_eval: n < 0");
     if (n == 0) return 0;

@@ -19,7 +19,7 @@ struct TcSetup {
     int n_node_tiles;
 };
 
-template <int D>
+template <int D, bool FMA_G2>
 __device__ __forceinline__ TcSetup tc_prologue(unsigned char* smem, const hepmc_elm_t& elm) {
     TcSetup u;
     u.n_node_tiles = (elm.nodes + TILE_N - 1) / TILE_N;
@@ -40,7 +40,7 @@ __device__ __forceinline__ TcSetup tc_prologue(unsigned char* smem, const hepmc_
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    build_tables<D>(u.s, elm.p0_dev, elm.p1_dev, elm.out_w_dev, elm.nodes, u.n_node_tiles);
+    build_tables<D, FMA_G2>(u.s, elm.p0_dev, elm.p1_dev, elm.out_w_dev, elm.nodes, u.n_node_tiles);
     fence_async_smem();   // tables were written through the generic proxy, the MMA reads them via the async proxy
     fence_before();
     __syncthreads();
@@ -58,12 +58,12 @@ __device__ __forceinline__ void tc_epilogue(const TcSetup& u) {
 }
 
 // ------------------------------------------------------------------ stand-alone gradient
-template <int D>
+template <int D, bool FMA_G2>
 __global__ void __launch_bounds__(N_THREADS, 1) elm_grad_tc_kernel(const __grid_constant__ hepmc_elm_t elm,
                                                                    const double* __restrict__ xs, int64_t n,
                                                                    double* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_tc[];
-    const TcSetup u = tc_prologue<D>(smem_tc, elm);
+    const TcSetup u = tc_prologue<D, FMA_G2>(smem_tc, elm);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
     const int64_t n_tiles = (n + TILE_M - 1) / TILE_M;
     // group of this warp; its barriers, TMEM columns and tiles (group g of CTA k: tiles 2k + g, stride 2 gridDim)
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) elm_grad_tc_kernel(const __grid_
             double x[D], g[D];
 #pragma unroll
             for (int k = 0; k < D; ++k) x[k] = j < n ? xs[j * D + k] : 0.5;
-            compute_eval<D>(st, gbars, lane_base, elm.nodes, u.n_node_tiles, dbg, x, g);
+            compute_eval<D, FMA_G2>(st, gbars, lane_base, elm.nodes, u.n_node_tiles, dbg, x, g, u.s.b2);
             if (j < n) {
 #pragma unroll
                 for (int k = 0; k < D; ++k) out[j * D + k] = g[k];
@@ -90,8 +90,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) elm_grad_tc_kernel(const __grid_
     } else {   // issuing warps: all lanes run the loop, one elected lane issues each instruction
         IssuerState st;
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
-            if (iss_q == 0) issuer_eval(st, gbars, gtmem, u.b1_saddr, u.b2_saddr, elm.nodes, u.n_node_tiles, dbg);
-            else aux_issuer_eval(st, gbars, gtmem, u.b2_saddr, elm.nodes, u.n_node_tiles, iss_q, dbg);
+            if constexpr (FMA_G2) {
+                if (iss_q == 0) issuer_eval_g1(st, gbars, gtmem, u.b1_saddr, elm.nodes, u.n_node_tiles, dbg);
+            } else {
+                if (iss_q == 0) issuer_eval(st, gbars, gtmem, u.b1_saddr, u.b2_saddr, elm.nodes, u.n_node_tiles, dbg);
+                else aux_issuer_eval(st, gbars, gtmem, u.b2_saddr, elm.nodes, u.n_node_tiles, iss_q, dbg);
+            }
         }
     }
     tc_epilogue(u);
@@ -99,13 +103,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) elm_grad_tc_kernel(const __grid_
 
 // ------------------------------------------------------------------ HMC with the tensor-core gradient
 // hmc.py:54-88, simulation.py:34-42 -- identical control flow to hmc_kernel in chains.cu
-template <int NDIM>
+template <int NDIM, bool FMA_G2>
 __global__ void __launch_bounds__(N_THREADS, 1) hmc_tc_kernel(const __grid_constant__ Dens dens,
                                                               const __grid_constant__ Dens pdist,
                                                               const __grid_constant__ hepmc_elm_t elm,
                                                               const __grid_constant__ ChainArgs a) {
     extern __shared__ __align__(128) unsigned char smem_tc[];
-    const TcSetup u = tc_prologue<NDIM>(smem_tc, elm);
+    const TcSetup u = tc_prologue<NDIM, FMA_G2>(smem_tc, elm);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
     const int64_t n_tiles = (a.n_chains + TILE_M - 1) / TILE_M;
     const int64_t evals_per_tile = (a.T - 1) * (int64_t)(a.steps + 1);
@@ -155,13 +159,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) hmc_tc_kernel(const __grid_const
                 }
 #pragma unroll
                 for (int d = 0; d < NDIM; ++d) { q[d] = x[d]; p[d] = p0[d]; }
-                compute_eval<NDIM>(cs, gbars, lane_base, elm.nodes, u.n_node_tiles, dbg, q, grad);
+                compute_eval<NDIM, FMA_G2>(cs, gbars, lane_base, elm.nodes, u.n_node_tiles, dbg, q, grad, u.s.b2);
                 for (int s = 0; s < a.steps; ++s) {
 #pragma unroll
                     for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
 #pragma unroll
                     for (int d = 0; d < NDIM; ++d) q[d] += a.step_size * (pdist.c[d] * (p[d] - pdist.a[d]));
-                    compute_eval<NDIM>(cs, gbars, lane_base, elm.nodes, u.n_node_tiles, dbg, q, grad);
+                    compute_eval<NDIM, FMA_G2>(cs, gbars, lane_base, elm.nodes, u.n_node_tiles, dbg, q, grad, u.s.b2);
 #pragma unroll
                     for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
                 }
@@ -203,8 +207,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) hmc_tc_kernel(const __grid_const
 #endif
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_step)
             for (int64_t e = 0; e < evals_per_tile; ++e) {
-                if (iss_q == 0) issuer_eval(st, gbars, gtmem, u.b1_saddr, u.b2_saddr, elm.nodes, u.n_node_tiles, dbg);
-                else aux_issuer_eval(st, gbars, gtmem, u.b2_saddr, elm.nodes, u.n_node_tiles, iss_q, dbg);
+                if constexpr (FMA_G2) {
+                    if (iss_q == 0) issuer_eval_g1(st, gbars, gtmem, u.b1_saddr, elm.nodes, u.n_node_tiles, dbg);
+                } else {
+                    if (iss_q == 0) issuer_eval(st, gbars, gtmem, u.b1_saddr, u.b2_saddr, elm.nodes, u.n_node_tiles, dbg);
+                    else aux_issuer_eval(st, gbars, gtmem, u.b2_saddr, elm.nodes, u.n_node_tiles, iss_q, dbg);
+                }
             }
     }
     tc_epilogue(u);
@@ -239,7 +247,8 @@ extern "C" int hepmc_tc_debug(int mode) {
     return (int)cudaMemcpyToSymbol(tc::g_tc_debug, &mode, sizeof(int));
 }
 
-int launch_elm_grad_tc(const hepmc_elm_t& elm, int ndim, const double* xs, int64_t n, double* out, cudaStream_t st) {
+int launch_elm_grad_tc(const hepmc_elm_t& elm, int ndim, const double* xs, int64_t n, double* out, bool fma_g2,
+                       cudaStream_t st) {
     size_t smem = 0;
     int e = tc_common_checks(elm, ndim, smem);
     if (e) return e;
@@ -248,8 +257,13 @@ int launch_elm_grad_tc(const hepmc_elm_t& elm, int ndim, const double* xs, int64
     const unsigned blocks = (unsigned)(pairs < sm_count() ? pairs : sm_count());
 #define GRAD_TC_CASE(ND)                                                                                           \
     do {                                                                                                           \
-        HEPMC_CUDA(cudaFuncSetAttribute(elm_grad_tc_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        elm_grad_tc_kernel<ND><<<blocks, tc::N_THREADS, smem, st>>>(elm, xs, n, out);                              \
+        if (fma_g2) {                                                                                              \
+            HEPMC_CUDA(cudaFuncSetAttribute(elm_grad_tc_kernel<ND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            elm_grad_tc_kernel<ND, true><<<blocks, tc::N_THREADS, smem, st>>>(elm, xs, n, out);                    \
+        } else {                                                                                                   \
+            HEPMC_CUDA(cudaFuncSetAttribute(elm_grad_tc_kernel<ND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            elm_grad_tc_kernel<ND, false><<<blocks, tc::N_THREADS, smem, st>>>(elm, xs, n, out);                   \
+        }                                                                                                          \
     } while (0)
     HEPMC_DISPATCH_TC_D(ndim, GRAD_TC_CASE);
 #undef GRAD_TC_CASE
@@ -257,7 +271,8 @@ int launch_elm_grad_tc(const hepmc_elm_t& elm, int ndim, const double* xs, int64
     return 0;
 }
 
-int launch_hmc_tc(const Dens& dens, const Dens& pdist, const hepmc_elm_t& elm, const ChainArgs& a, cudaStream_t st) {
+int launch_hmc_tc(const Dens& dens, const Dens& pdist, const hepmc_elm_t& elm, const ChainArgs& a, bool fma_g2,
+                  cudaStream_t st) {
     size_t smem = 0;
     int e = tc_common_checks(elm, dens.ndim, smem);
     if (e) return e;
@@ -266,8 +281,13 @@ int launch_hmc_tc(const Dens& dens, const Dens& pdist, const hepmc_elm_t& elm, c
     const unsigned blocks = (unsigned)(pairs < sm_count() ? pairs : sm_count());
 #define HMC_TC_CASE(ND)                                                                                            \
     do {                                                                                                           \
-        HEPMC_CUDA(cudaFuncSetAttribute(hmc_tc_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        hmc_tc_kernel<ND><<<blocks, tc::N_THREADS, smem, st>>>(dens, pdist, elm, a);                               \
+        if (fma_g2) {                                                                                              \
+            HEPMC_CUDA(cudaFuncSetAttribute(hmc_tc_kernel<ND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            hmc_tc_kernel<ND, true><<<blocks, tc::N_THREADS, smem, st>>>(dens, pdist, elm, a);                     \
+        } else {                                                                                                   \
+            HEPMC_CUDA(cudaFuncSetAttribute(hmc_tc_kernel<ND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            hmc_tc_kernel<ND, false><<<blocks, tc::N_THREADS, smem, st>>>(dens, pdist, elm, a);                    \
+        }                                                                                                          \
     } while (0)
     HEPMC_DISPATCH_TC_D(dens.ndim, HMC_TC_CASE);
 #undef HMC_TC_CASE

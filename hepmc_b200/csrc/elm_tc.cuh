@@ -279,7 +279,17 @@ __device__ __forceinline__ Shared carve_tc(unsigned char* base, int n_tiles) {
 enum { BAR_A = 0, BAR_D2 = 1, BAR_S0 = 2, BAR_P0 = 2 + N_SBUF, BAR_G0 = 2 + 2 * N_SBUF };
 
 // Build the resident node tables (all threads).  centers (I, D), widths (I,), out_w (I,).
-template <int D>
+// FMA_G2 = true ("tc32" mode): the contraction with B2 runs in FP32 on the FMA pipe, so the B2
+// region holds plain FP32 values w[n] = [coef c'_0 .. coef c'_{D-1}, coef, 0] per node
+// (read with warp-uniform, i.e. broadcast, LDS) instead of the TF32 MMA tile.  The contraction is
+// bound by the LDS write-back into registers (D + 1 floats per lane and node), not by the FMA
+// issue: packed fma.rn.f32x2 with node-pair interleaved rows was measured no faster / slower
+// (26.9 k / 30.0 k vs 27.1 k cycles per evaluation at I = 1024), so the plain form stays and
+// only the D + 1 used floats of a row are loaded.
+constexpr int B2F_ROW = 12;
+static_assert(TILE_N * B2F_ROW * 4 <= B2_TILE_BYTES && MAX_D + 1 <= B2F_ROW, "FP32 B2 rows fit the B2 tile");
+
+template <int D, bool FMA_G2 = false>
 __device__ __forceinline__ void build_tables(const Shared& s, const double* __restrict__ centers,
                                              const double* __restrict__ widths, const double* __restrict__ out_w,
                                              int nodes, int n_tiles) {
@@ -303,11 +313,11 @@ __device__ __forceinline__ void build_tables(const Shared& s, const double* __re
                 const double c = centers[(size_t)i * D + k] - 0.5;
                 c2 += c * c;
                 vals[k] = 2.0 * h * L2E * c;
-                b2v[k] = __uint_as_float(to_tf32_rna((float)(coef * c)));
+                b2v[k] = FMA_G2 ? (float)(coef * c) : __uint_as_float(to_tf32_rna((float)(coef * c)));
             }
             vals[D] = -h * L2E;
             vals[D + 1] = -h * L2E * c2;
-            b2v[D] = __uint_as_float(to_tf32_rna((float)coef));
+            b2v[D] = FMA_G2 ? (float)coef : __uint_as_float(to_tf32_rna((float)coef));
         } else {  // padding node: S = -1e4 -> P = 0
 #pragma unroll
             for (int k = 0; k < D + 1; ++k) vals[k] = 0.0;
@@ -327,9 +337,14 @@ __device__ __forceinline__ void build_tables(const Shared& s, const double* __re
             *reinterpret_cast<float4*>(b1t + ((size_t)c * TILE_N + r) * 4) =
                 make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         float* b2t = s.b2 + (size_t)t * (B2_TILE_BYTES / 4);
-        const int chunk = r >> 2, within = r & 3;
+        if constexpr (FMA_G2) {
 #pragma unroll
-        for (int n = 0; n < N2; ++n) b2t[((size_t)chunk * N2 + n) * 4 + within] = b2v[n];
+            for (int n = 0; n < B2F_ROW; ++n) b2t[r * B2F_ROW + n] = b2v[n];
+        } else {
+            const int chunk = r >> 2, within = r & 3;
+#pragma unroll
+            for (int n = 0; n < N2; ++n) b2t[((size_t)chunk * N2 + n) * 4 + within] = b2v[n];
+        }
     }
 }
 
@@ -424,6 +439,31 @@ __device__ __forceinline__ void issuer_eval(IssuerState& st, uint32_t bars, uint
     }
     umma_commit(bars + 8 * BAR_D2);
     HEPMC_TRACE(st, 4096, 15, -1);
+}
+
+// "tc32" mode: only GEMM-1 is issued; BAR_P0 + b means "S[b] has been read into registers"
+__device__ __forceinline__ void issuer_eval_g1(IssuerState& st, uint32_t bars, uint32_t tmem_base, uint32_t b1_saddr,
+                                               int nodes, int n_tiles, int dbg) {
+    mbar_wait(bars + 8 * BAR_A, st.ph_a);
+    st.ph_a ^= 1;
+    fence_after();
+#pragma unroll
+    for (int b = 0; b < N_SBUF; ++b) {
+        if (b < n_tiles) {
+            issue_g1(tmem_base, b1_saddr, b, tile_cols(nodes, b), dbg);
+            umma_commit(bars + 8 * (BAR_S0 + b));
+        }
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+        const int b = t % N_SBUF;
+        mbar_wait(bars + 8 * (BAR_P0 + b), st.ph_p[b]);
+        st.ph_p[b] ^= 1;
+        if (t + N_SBUF < n_tiles) {
+            fence_after();
+            issue_g1(tmem_base, b1_saddr, t + N_SBUF, tile_cols(nodes, t + N_SBUF), dbg);
+            umma_commit(bars + 8 * (BAR_S0 + b));
+        }
+    }
 }
 
 // issuers 1 .. N_ISS-1 of a group: their share of GEMM-2
@@ -563,9 +603,70 @@ __device__ __forceinline__ void exp_tiles(ComputeState& st, uint32_t bars, uint3
     HEPMC_TRACE(st, 0, 3, n_tiles - 1);
 }
 
+// "tc32" mode: P = exp2(S) stays in registers and is contracted with the FP32 B2 rows on the FMA
+// pipe (D + 1 FFMA per pair): acc[n] += P_ji * b2f[i][n].  Same chunk stream as exp_tiles; a tile's
+// S buffer is released (BAR_P0 + b) as soon as its last chunk is in registers.
 template <int D>
+__device__ __forceinline__ void exp_fma_tiles(ComputeState& st, uint32_t bars, uint32_t tmem_lane_base,
+                                              const float* __restrict__ b2f, int nodes, int n_tiles, float (&acc)[D + 1]) {
+#pragma unroll
+    for (int n = 0; n <= D; ++n) acc[n] = 0.f;
+    uint32_t va[16], vb[16];
+    mbar_wait(bars + 8 * BAR_S0, st.ph_s[0]);
+    st.ph_s[0] ^= 1;
+    fence_after();
+    tmem_ld16(tmem_lane_base + COL_S0, va);
+    for (int t = 0; t < n_tiles; ++t) {
+        const int b = t % N_SBUF;
+        const uint32_t col = COL_S0 + b * TILE_N;
+        const int nch = tile_cols(nodes, t) >> 4;
+        const bool more = t + 1 < n_tiles;
+        const int nb = (t + 1) % N_SBUF;
+        const float* rows = b2f + (size_t)t * (B2_TILE_BYTES / 4);
+#pragma unroll
+        for (int c = 0; c < TILE_N / 16; ++c) {
+            if (c < nch) {
+                uint32_t(&cur)[16] = (c & 1) ? vb : va;
+                uint32_t(&oth)[16] = (c & 1) ? va : vb;
+                tmem_wait_ld();
+                if (c + 1 < nch) {
+                    tmem_ld16(tmem_lane_base + col + (c + 1) * 16, oth);
+                } else {
+                    // the whole tile is in registers: release its buffer, then start on the next tile
+                    fence_before();
+                    __syncwarp();
+                    if ((threadIdx.x & 31) == 0) mbar_arrive(bars + 8 * (BAR_P0 + b));
+                    if (more) {
+                        mbar_wait(bars + 8 * (BAR_S0 + nb), st.ph_s[nb]);
+                        st.ph_s[nb] ^= 1;
+                        fence_after();
+                        tmem_ld16(tmem_lane_base + COL_S0 + nb * TILE_N, oth);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float p = ex2_approx(__uint_as_float(cur[j]));
+                    const float* row = rows + (c * 16 + j) * B2F_ROW;
+                    float w[B2F_ROW];
+#pragma unroll
+                    for (int q = 0; q < (D + 1) / 4; ++q) {
+                        const float4 v = reinterpret_cast<const float4*>(row)[q];
+                        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int n = ((D + 1) / 4) * 4; n <= D; ++n) w[n] = row[n];
+#pragma unroll
+                    for (int n = 0; n <= D; ++n) acc[n] = fmaf(p, w[n], acc[n]);
+                }
+            }
+        }
+    }
+}
+
+template <int D, bool FMA_G2 = false>
 __device__ __forceinline__ void compute_eval(ComputeState& st, uint32_t bars, uint32_t tmem_lane_base, int nodes,
-                                             int n_tiles, int dbg, const double (&x)[D], double (&g)[D]) {
+                                             int n_tiles, int dbg, const double (&x)[D], double (&g)[D],
+                                             const float* __restrict__ b2f = nullptr) {
     // A1 row: [hi(a), hi(a), lo(a)] with a = [x', |x'|^2, 1]; single precision is enough for the
     // split (hi + lo carries 22 bits), the double -> float conversion happens once per coordinate
     uint32_t a1[32];
@@ -609,6 +710,13 @@ __device__ __forceinline__ void compute_eval(ComputeState& st, uint32_t bars, ui
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(bars + 8 * BAR_A);  // one arrival per warp
     HEPMC_TRACE(st, 0, 5, -1);
+    if constexpr (FMA_G2) {
+        float accf[D + 1];
+        exp_fma_tiles<D>(st, bars, tmem_lane_base, b2f, nodes, n_tiles, accf);
+#pragma unroll
+        for (int k = 0; k < D; ++k) g[k] = (double)(accf[k] - xc[k] * accf[D]);
+        return;
+    }
     exp_tiles(st, bars, tmem_lane_base, nodes, n_tiles, dbg);
     mbar_wait(bars + 8 * BAR_D2, st.ph_d2);
     st.ph_d2 ^= 1;

@@ -18,8 +18,8 @@ from .simulation import HamiltonLeapfrog
 from .. import _lib
 
 
-# cancellation ratio of the surrogate gradient above which precision='tc' warns (measured:
-# <= ~300 is harmless, ~1e4 halves the acceptance rate; scripts/tc_conditioning.py)
+# cancellation ratio of the surrogate gradient above which precision='tc' switches to 'tc32'
+# (measured: <= ~300 is harmless for TF32, ~1e4 halves the acceptance rate; scripts/tc_conditioning.py)
 TC_CANCELLATION_LIMIT = 2000.0
 
 
@@ -28,8 +28,10 @@ class HamiltonianUpdate(MetropolisUpdate):
     def __init__(self, target_density, p_dist, steps, step_size, simulate=None,
                  sim_class=HamiltonLeapfrog, is_adaptive=False, precision="f64"):
         """:param precision: arithmetic of a SURROGATE gradient: "f64" (parity), "f32"
-        (SIMT single precision) or "tc" (tcgen05 tensor cores).  The exact gradient and
-        the Metropolis test are always float64."""
+        (SIMT single precision), "tc" (tcgen05 tensor cores for both GEMMs, TF32 operands in the
+        contraction; switches itself to "tc32" when the trained weights cancel too heavily for
+        TF32) or "tc32" (tensor cores for the exponent GEMM, FP32 contraction on the FMA pipe:
+        float32-level accuracy).  The exact gradient and the Metropolis test are always float64."""
         super().__init__(target_density.ndim, target_density.pdf, is_adaptive)
         self.p_dist = p_dist
         self.target_density = target_density
@@ -77,19 +79,22 @@ class HamiltonianUpdate(MetropolisUpdate):
                 raise TypeError("a replaced pot_gradient must be a surrogate.SurrogateGradient "
                                 "(ELM surrogate); arbitrary Python gradients cannot run in the kernel")
             elm_blk, keep = grad.block()
-        prec = {"f64": 0, "f32": 1, "tc": 2}[self.precision]
+        prec = {"f64": 0, "f32": 1, "tc": 2, "tc32": 3}[self.precision]
         if elm_blk is None:
             prec = 0
-        if prec == 2 and not getattr(self, "_tc_checked", False):
-            # one-time guard: TF32 operands cannot resolve a heavily cancelling weight vector
-            self._tc_checked = True
-            kappa = grad.cancellation(x0[:256])
-            if kappa > TC_CANCELLATION_LIMIT:
-                import warnings
-                warnings.warn("precision='tc': the surrogate's gradient sum cancels by a factor %.0f (> %.0f); TF32 "
-                              "operands lose it and the acceptance rate will drop (the sampler stays exact).  Retrain "
-                              "with extreme_learning_train(..., ridge=1e-6) or use precision='f32'."
-                              % (kappa, TC_CANCELLATION_LIMIT), RuntimeWarning, stacklevel=3)
+        if prec == 2:
+            # TF32 operands in the contraction cannot resolve a heavily cancelling weight vector:
+            # measure the cancellation once and fall back to the FP32 contraction ("tc32") above the limit
+            if getattr(self, "_tc_mode", None) is None:
+                kappa = grad.cancellation(x0[:256])
+                self._tc_mode = 3 if kappa > TC_CANCELLATION_LIMIT else 2
+                if self._tc_mode == 3:
+                    import warnings
+                    warnings.warn("precision='tc': the surrogate's gradient sum cancels by a factor %.0f (> %.0f), which "
+                                  "TF32 operands would lose; using precision='tc32' (tensor cores for the exponents, "
+                                  "FP32 contraction) instead.  extreme_learning_train(..., ridge=1e-6) avoids the "
+                                  "cancellation." % (kappa, TC_CANCELLATION_LIMIT), RuntimeWarning, stacklevel=3)
+            prec = self._tc_mode
         out = ensemble.run_hmc(tgt._block(), elm_blk, prec, x0, mass, self.step_size, self.steps,
                                sample_size, thin, store_chain, first_chain, None, replay)
         del keep

@@ -269,8 +269,11 @@ typedef struct hepmc_elm {
 /* mass_host[ndim] = diag of the momentum covariance.  Momentum tape p_replay_dev
  * (n_chains, T-1, ndim) holds the momenta themselves.  Other arguments as hepmc_rwm_chains.
  * precision: 0 = float64 everywhere (parity mode); 1 = surrogate gradient in float32
- * SIMT; 2 = surrogate gradient on tcgen05 tensor cores (TF32 operands, FP32 accumulate).
- * The Metropolis test always uses the float64 target pdf, so 1 and 2 stay exact samplers. */
+ * SIMT; 2 = surrogate gradient on tcgen05 tensor cores (TF32 operands, FP32 accumulate) in both
+ * GEMMs: every term of the gradient sum carries ~2^-11 relative error, fine while the trained
+ * weights cancel by less than ~1e3; 3 = exponent GEMM on the tensor cores (3xTF32), contraction
+ * with the output weights in FP32 on the FMA pipe (float32-level accuracy for any weights).
+ * The Metropolis test always uses the float64 target pdf, so 1, 2 and 3 stay exact samplers. */
 int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int precision,
                      const double* x0_dev, const double* mass_host, double step_size, int steps,
                      int64_t n_chains, int64_t first_chain, int64_t sample_size, int64_t thin,

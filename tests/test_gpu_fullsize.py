@@ -93,8 +93,8 @@ def test_c5_hmc_elm_full_size_precisions_agree():
     leapfrog: float64, float32 and tensor-core gradients give the same acceptance rate (the
     Metropolis test uses the float64 pdf in all three) and the same ensemble moments -- for a
     surrogate whose gradient sum does not cancel by more than ~1e3 (ridge-regularised training).
-    The reference's plain pseudo-inverse at this node count cancels by ~1e4: float32 still
-    agrees, the TF32 path warns and loses acceptance (HMC stays exact, only less efficient)."""
+    The reference's plain pseudo-inverse at this node count cancels by ~1e4: float32 and the
+    "tc32" mode (FP32 contraction) still agree; "tc" detects the cancellation, warns and runs tc32."""
     import warnings
     H.set_outputs("torch")
     try:
@@ -110,7 +110,7 @@ def test_c5_hmc_elm_full_size_precisions_agree():
         def run(ridge):
             params, bias, w = basis.extreme_learning_train(xs, tgt0.pot(xs), nodes, params=hidden, ridge=ridge)
             rates, means, kappa, warned = {}, {}, None, False
-            for prec in ("f64", "f32", "tc"):
+            for prec in ("f64", "f32", "tc32", "tc"):
                 H.seed(77)
                 tgt = H.densities.Camel(8)
                 grad = H.surrogate.attach_surrogate_gradient(tgt, basis, params, bias, w)
@@ -129,8 +129,11 @@ def test_c5_hmc_elm_full_size_precisions_agree():
         assert rates["f64"] > 0.6, rates
         assert abs(rates["f32"] - rates["f64"]) < 0.005 and abs(rates["tc"] - rates["f64"]) < 0.01, rates
         assert np.allclose(means["f32"], means["f64"], atol=2e-3) and np.allclose(means["tc"], means["f64"], atol=2e-3)
+        assert abs(rates["tc32"] - rates["f64"]) < 0.005 and np.allclose(means["tc32"], means["f64"], atol=2e-3)
+        # plain pseudo-inverse: "tc" notices the cancellation, warns and runs the tc32 kernel
         rates, means, kappa, warned = run(0.0)
         assert kappa > H.hamiltonian.hmc.TC_CANCELLATION_LIMIT and warned, kappa
-        assert abs(rates["f32"] - rates["f64"]) < 0.005 and rates["tc"] < rates["f64"], rates
+        assert abs(rates["f32"] - rates["f64"]) < 0.005, rates
+        assert abs(rates["tc32"] - rates["f64"]) < 0.01 and rates["tc"] == rates["tc32"], rates
     finally:
         H.set_outputs("numpy")

@@ -729,8 +729,30 @@ def test_elm_gradient_on_tensor_cores():
             scale = np.sum(np.abs((p * (w / widths ** 2))[:, :, None] * diff), axis=1)
             assert np.all(err <= 1.5e-3 * scale + 1e-30), (nodes, ndim, J, float(np.max(err / (scale + 1e-300))))
     # far-away / non-finite points give a finite (zero) surrogate gradient, not a hang or NaN
-    g = basis.eval_gradient(params, 0.0, w, np.array([[1e9, -1e9], [np.inf, 0.3], [np.nan, 0.1]]), precision=2)
-    assert np.all(np.isfinite(g))
+    for prec in (2, 3):
+        g = basis.eval_gradient(params, 0.0, w, np.array([[1e9, -1e9], [np.inf, 0.3], [np.nan, 0.1]]), precision=prec)
+        assert np.all(np.isfinite(g))
+
+
+def test_elm_gradient_tc32_mode():
+    """precision 3 ("tc32"): exponent GEMM on the tensor cores (3xTF32), contraction in FP32 on the
+    FMA pipe.  The error against float64 is relative to the SUM OF TERM MAGNITUDES at the level of
+    the exponent accuracy (h |x-c|^2 resolved to ~2^-21 of its largest term), so heavily
+    cancelling weights are handled like the float32 kernel handles them."""
+    rs = np.random.default_rng(4)
+    for nodes, ndim in ((100, 8), (64, 3), (65, 8), (192, 1), (257, 7), (1024, 8), (17, 2)):
+        basis = H.surrogate.GaussianBasis(ndim)
+        centers, widths = rs.random((nodes, ndim)), 0.05 + 0.95 * rs.random(nodes)
+        params = (centers, widths, None)
+        w = rs.standard_normal(nodes) * 10.0 ** rs.integers(0, 5, nodes)       # alternating, 1 .. 1e4
+        for J in (1, 128, 257, 3000):
+            xs = rs.random((J, ndim))
+            g64 = basis.eval_gradient(params, 0.0, w, xs, precision=0)
+            g3 = basis.eval_gradient(params, 0.0, w, xs, precision=3)
+            diff = xs[:, None, :] - centers[None, :, :]
+            p = np.exp(-np.sum(diff ** 2, axis=2) / (2 * widths ** 2))
+            scale = np.sum(np.abs((p * (w / widths ** 2))[:, :, None] * diff), axis=1)
+            assert np.all(np.abs(g3 - g64) <= 2e-5 * scale + 1e-30), (nodes, ndim, J, float(np.max(np.abs(g3 - g64) / (scale + 1e-300))))
 
 
 def test_hmc_tensor_core_surrogate_is_an_exact_sampler():
