@@ -359,6 +359,20 @@ def other_workloads(H, _lib, torch, fp64_peak, with_cpu, rank=0, world=1):
         t = timed(lambda: mc2(camel2, 100_000, 10, keep_samples=False))
         out["c1_vegas2"] = {"metric": "camel-2D VEGAS points/s (10 x 1e5 points, whole call)", "value": 1e6 / t,
                             "cpu_baseline": cpu.get("vegas2")}
+        # the reference's default mode keeps every point: data + function values (+ weights) are
+        # written out, so these two are read against HBM (outputs of 7 GB / 14 GB, larger than L2)
+        camel16 = H.densities.Camel(16)
+        nk = 50_000_000
+        t = timed(lambda: H.PlainMC(16)(camel16, nk, keep_samples=True))
+        out["plain16_keep"] = {"metric": "camel-16D plain MC points/s, keep_samples=True (5e7 points)", "value": nk / t,
+                               "roofline": {"bound": "hbm", "achieved": nk * 17 * 8 / t / 1e9, "peak": hbm, "unit": "GB/s",
+                                            "frac": nk * 17 * 8 / t / 1e9 / hbm, "bytes_per_point": 136}}
+        mck = H.VegasMC(16, divisions=15)
+        t = timed(lambda: mck(camel16, nk, 2, keep_samples=True))
+        out["vegas16_keep"] = {"metric": "camel-16D VEGAS points/s, keep_samples=True (2 x 5e7 points)", "value": 2 * nk / t,
+                               "roofline": {"bound": "hbm", "achieved": 2 * nk * 18 * 8 / t / 1e9, "peak": hbm, "unit": "GB/s",
+                                            "frac": 2 * nk * 18 * 8 / t / 1e9 / hbm, "bytes_per_point": 144}}
+        del mck
     # C2: RAMBO 2->4, sqrt(s) = 100 GeV: 2^27 points per launch whole job (16 GiB of output,
     # larger than L2 at every N)
     m = H.phase_space.Rambo(100., 4)

@@ -111,12 +111,23 @@ class VegasMC(object):
         sid0 = rng.next_stream(iterations)
         blk = dens._block() if fused else engine.none_block(ndim)
         need_pts = keep_samples or not fused
-        kept = {"data": [], "function_values": [], "weights": []}
+        kept = None
+        if keep_samples and iterations:
+            # the kernels write every iteration straight into its slice of the returned arrays
+            # (data is (ndim * iterations, N): the reference's transposed layout, vegas.py:105)
+            kept = {"data": torch.empty((iterations * ndim, n_local), dtype=torch.float64, device=dev),
+                    "function_values": torch.empty(iterations * n_local, dtype=torch.float64, device=dev),
+                    "weights": torch.empty(iterations * n_local, dtype=torch.float64, device=dev)}
         st = _lib.stream_ptr()
         for j in range(iterations):
-            x = torch.empty((ndim, n_local), dtype=torch.float64, device=dev) if need_pts else None
-            w = torch.empty(n_local, dtype=torch.float64, device=dev) if need_pts else None
-            f = torch.empty(n_local, dtype=torch.float64, device=dev) if (keep_samples and fused) else None
+            if kept is not None:
+                x = kept["data"][j * ndim:(j + 1) * ndim]
+                w = kept["weights"][j * n_local:(j + 1) * n_local]
+                f = kept["function_values"][j * n_local:(j + 1) * n_local] if fused else None
+            else:
+                x = torch.empty((ndim, n_local), dtype=torch.float64, device=dev) if need_pts else None
+                w = torch.empty(n_local, dtype=torch.float64, device=dev) if need_pts else None
+                f = None
             idx = torch.empty((ndim, n_local), dtype=torch.int64, device=dev) if not fused else None
             if n_local:
                 _lib.call("hepmc_vegas_sample", ctypes.byref(blk), _lib.ptr(grid), ndim, K, n_local, first, chunk,
@@ -141,11 +152,9 @@ class VegasMC(object):
                 slot_stats, slot_hist = slot_stats_l, slot_hist_l
             _lib.call("hepmc_vegas_update_grid", _lib.ptr(slot_stats), _lib.ptr(slot_hist), slot_stats.shape[0],
                       _lib.ptr(grid), ndim, K, float(self.c), j, _lib.ptr(est_var), st)
-            if keep_samples:
-                kept["data"].append(x)
-                kept["function_values"].append(f)
-                kept["weights"].append(w)
-        return self._combine(est_var, n_total, iterations, chi, kept if keep_samples else None)
+            if kept is not None and not fused and n_local:
+                kept["function_values"][j * n_local:(j + 1) * n_local] = f
+        return self._combine(est_var, n_total, iterations, chi, kept)
 
     def _combine(self, est_var, n_total, iterations, chi, kept):
         """Combination of the iterations, vegas.py:124-142 (host scalars)."""
@@ -166,7 +175,7 @@ class VegasMC(object):
         if chi:
             sample.chi2 = float(np.sum((est_j - total_est) ** 2 / var_j) / (iterations - 1))
         if kept is not None and iterations:
-            sample.data = config.deliver(torch.cat(kept["data"], dim=0))
-            sample.function_values = config.deliver(torch.cat(kept["function_values"], dim=0))
-            sample.weights = config.deliver(torch.cat(kept["weights"], dim=0))
+            sample.data = config.deliver(kept["data"])
+            sample.function_values = config.deliver(kept["function_values"])
+            sample.weights = config.deliver(kept["weights"])
         return sample

@@ -275,18 +275,20 @@ static int check_sample_common(const char* who, int ndim, int K, int64_t n, int6
         }                                                                                                   \
         break;
 
-// fast = native RNG and no per-point outputs: compile-time (kind, ndim) instance when one
-// exists (ndim <= 16), else the generic kernel (runtime ndim and flags).
+// fast = native RNG: compile-time (kind, ndim) instance when one exists (ndim <= 16), with or
+// without per-point outputs; else the generic kernel (runtime ndim, replay tapes).
 static int launch_sample(bool vegas, bool fast, const Dens& dens, const SampleArgs& a, unsigned blocks, int threads,
                          size_t smem, cudaStream_t st) {
     if (fast) {
+        const bool out = a.x_out || a.f_out || a.w_out || a.idx_out;
         int e = -100;
         switch (dens.kind) {
-            case HEPMC_CAMEL: e = launch_fast_camel(vegas, a.ndim, dens, a, blocks, threads, smem, st); break;
-            case HEPMC_UCAMEL: e = launch_fast_ucamel(vegas, a.ndim, dens, a, blocks, threads, smem, st); break;
-            case HEPMC_BANANA: e = launch_fast_banana(vegas, a.ndim, dens, a, blocks, threads, smem, st); break;
-            case HEPMC_GAUSSIAN: e = launch_fast_gaussian(vegas, a.ndim, dens, a, blocks, threads, smem, st); break;
-            case HEPMC_UNIFORM: e = launch_fast_uniform(vegas, a.ndim, dens, a, blocks, threads, smem, st); break;
+            case HEPMC_CAMEL: e = launch_fast_camel(vegas, out, a.ndim, dens, a, blocks, threads, smem, st); break;
+            case HEPMC_UCAMEL: e = launch_fast_ucamel(vegas, out, a.ndim, dens, a, blocks, threads, smem, st); break;
+            case HEPMC_BANANA: e = launch_fast_banana(vegas, out, a.ndim, dens, a, blocks, threads, smem, st); break;
+            case HEPMC_GAUSSIAN: e = launch_fast_gaussian(vegas, out, a.ndim, dens, a, blocks, threads, smem, st); break;
+            case HEPMC_UNIFORM: e = launch_fast_uniform(vegas, out, a.ndim, dens, a, blocks, threads, smem, st); break;
+            case HEPMC_NONE: e = launch_fast_none(vegas, out, a.ndim, dens, a, blocks, threads, smem, st); break;
             default: break;
         }
         if (e != -100) return e;
@@ -333,7 +335,7 @@ int hepmc_plain_mc_sample(const hepmc_density_t* dens, int64_t n, int64_t first_
     a.seed = seed; a.stream_id = stream_id; a.u_replay = u_replay_dev;
     a.x_out = data_dev; a.f_out = f_dev; a.stats_partials = partials_dev;
     const int64_t blocks = (n + chunk - 1) / chunk;
-    const bool fast = dens->kind != HEPMC_NONE && !u_replay_dev && !data_dev && !f_dev;
+    const bool fast = !u_replay_dev;   // native draws: templated instance, with outputs if any pointer is given
     int e2 = launch_sample(false, fast, *dens, a, (unsigned)blocks, 256, 0, as_stream(stream));
     if (e2) return e2;
     HEPMC_LAUNCH_CHECK();
@@ -406,7 +408,7 @@ int hepmc_vegas_sample(const hepmc_density_t* dens, const double* grid_dev, int 
     a.stats_partials = stats_partials_dev; a.hist_partials = hist_partials_dev;
     a.kpow = pow((double)divisions, (double)ndim);
     const int64_t blocks = (n + chunk - 1) / chunk;
-    const bool fast = fused && !u_replay_dev && !x_dev && !f_dev && !w_dev && !idx_dev;
+    const bool fast = !u_replay_dev;   // native draws: templated instance, with outputs if any pointer is given
     int e2 = launch_sample(true, fast, *dens, a, (unsigned)blocks, threads, smem, as_stream(stream));
     if (e2) return e2;
     HEPMC_LAUNCH_CHECK();

@@ -1,6 +1,8 @@
 // Kernel templates of the integration path, shared by integrate.cu (generic instances:
 // runtime ndim, replay tapes, per-point outputs) and integrate_fast_*.cu (throughput
-// instances: compile-time ndim and density kind, native RNG, no per-point outputs).
+// instances: compile-time ndim and density kind, native RNG; one instance without and one with
+// per-point outputs -- keep_samples=True, the reference's default -- per (kind, ndim), and
+// sample-only instances (kind NONE) for user integrands).
 #pragma once
 #include "density.cuh"
 
@@ -141,8 +143,8 @@ __device__ __forceinline__ SmemLayout carve(double* base, int ndim, int K, int n
 // FAST: native RNG, no per-point outputs (the throughput path); otherwise replay tapes and
 //       x / f / w / idx outputs are honoured through warp-uniform runtime flags.
 // Shared grid layout: per axis K entries of (bound_k, size_k) as double2 -> one LDS.128.
-template <int KIND, int NDIM_T, bool FAST>
-__global__ void __launch_bounds__(256, FAST ? kFastMinBlocks : 1) vegas_sample_kernel(const __grid_constant__ Dens dens,
+template <int KIND, int NDIM_T, bool FAST, bool OUT = !FAST>
+__global__ void __launch_bounds__(256, (FAST && !OUT) ? kFastMinBlocks : (FAST ? 2 : 1)) vegas_sample_kernel(const __grid_constant__ Dens dens,
                                                            const __grid_constant__ SampleArgs a) {
     extern __shared__ double smem_raw[];
     const int ndim = NDIM_T ? NDIM_T : a.ndim;
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(256, FAST ? kFastMinBlocks : 1) vegas_sample_k
     // one sample point: draws -> grid map -> integrand -> weight; returns f*w and the packed bins
     auto point = [&](int64_t li, double& wf, uint32_t (&packed)[NPACK]) {
         const uint64_t g = (uint64_t)(a.first_index + li);
+        const bool ok = li < a.n;   // the FAST loop also runs the padding points of the last chunk: they store nothing
         PdfAcc pa;
         pa.init();
         double w = 1.0;
@@ -210,22 +213,22 @@ __global__ void __launch_bounds__(256, FAST ? kFastMinBlocks : 1) vegas_sample_k
                         for (int q = 0; q < NPACK; ++q)
                             if (q == (d >> 2)) packed[q] |= bin << (8 * (d & 3));
                     }
-                    if constexpr (!FAST) {
-                        if (a.x_out) a.x_out[(int64_t)d * a.n + li] = x;
-                        if (a.idx_out) a.idx_out[(int64_t)d * a.n + li] = (int64_t)bin;
+                    if constexpr (OUT) {
+                        if (a.x_out && ok) a.x_out[(int64_t)d * a.n + li] = x;
+                        if (a.idx_out && ok) a.idx_out[(int64_t)d * a.n + li] = (int64_t)bin;
                     }
                 }
             }
         }
         w *= a.kpow;  // vegas.py:72 (partition_count evaluated in floating point, App. B1)
-        if constexpr (!FAST) {
-            if (a.w_out) a.w_out[li] = w;
+        if constexpr (OUT) {
+            if (a.w_out && ok) a.w_out[li] = w;
         }
         if constexpr (fused) {
             const double f = pdf_acc_finish<KIND>(dens, pa);
             wf = f * w;  // vegas.py:104
-            if constexpr (!FAST) {
-                if (a.f_out) a.f_out[li] = f;
+            if constexpr (OUT) {
+                if (a.f_out && ok) a.f_out[li] = f;
             }
         }
     };
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(256, FAST ? kFastMinBlocks : 1) vegas_sample_k
 }
 
 // ------------------------------------------------------------------ plain MC
-template <int KIND, int NDIM_T, bool FAST>
+template <int KIND, int NDIM_T, bool FAST, bool OUT = !FAST>
 __global__ void __launch_bounds__(256) plain_sample_kernel(const __grid_constant__ Dens dens,
                                                            const __grid_constant__ SampleArgs a) {
     __shared__ Stats s_stats[8];
@@ -302,6 +305,7 @@ __global__ void __launch_bounds__(256) plain_sample_kernel(const __grid_constant
         const uint64_t g = (uint64_t)(a.first_index + li);
         PdfAcc pa;
         pa.init();
+        double xrow[NDIM_T ? NDIM_T : 1];
 #pragma unroll
         for (int call = 0; call < ncalls; ++call) {
             U4 r{0u, 0u, 0u, 0u};
@@ -318,16 +322,37 @@ __global__ void __launch_bounds__(256) plain_sample_kernel(const __grid_constant
                         if constexpr (FAST) pdf_acc_dim<KIND, 0>(dens, pa, d, x);
                         else pdf_acc_dim<KIND, 2>(dens, pa, d, x);
                     }
-                    if constexpr (!FAST) {
-                        if (a.x_out) a.x_out[li * ndim + d] = x;  // (N, ndim) row-major, integration.py:45
+                    if constexpr (OUT) {
+                        // (N, ndim) row-major, integration.py:45.  Compile-time ndim: the row is staged in
+                        // registers and leaves as 256- / 128-bit stores (one contiguous 8 ndim byte run per
+                        // thread); scalar stores of a 128-byte-strided row reach a third of the bandwidth.
+                        if constexpr (NDIM_T != 0) xrow[d] = x;
+                        else if (a.x_out) a.x_out[li * ndim + d] = x;
                     }
+                }
+            }
+        }
+        if constexpr (OUT && NDIM_T != 0) {
+            if (a.x_out) {
+                double* row = a.x_out + li * NDIM_T;
+                if constexpr (NDIM_T % 4 == 0) {
+#pragma unroll
+                    for (int d = 0; d < NDIM_T; d += 4)
+                        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(row + d), "d"(xrow[d]), "d"(xrow[d + 1]),
+                                     "d"(xrow[d + 2]), "d"(xrow[d + 3]) : "memory");
+                } else if constexpr (NDIM_T % 2 == 0) {
+#pragma unroll
+                    for (int d = 0; d < NDIM_T; d += 2) *reinterpret_cast<double2*>(row + d) = make_double2(xrow[d], xrow[d + 1]);
+                } else {
+#pragma unroll
+                    for (int d = 0; d < NDIM_T; ++d) row[d] = xrow[d];
                 }
             }
         }
         if constexpr (fused) {
             const double f = pdf_acc_finish<KIND>(dens, pa);
             acc.add(f);
-            if constexpr (!FAST) {
+            if constexpr (OUT) {
                 if (a.f_out) a.f_out[li] = f;
             }
         }
@@ -346,17 +371,17 @@ __global__ void __launch_bounds__(256) plain_sample_kernel(const __grid_constant
 
 
 // fast-path launchers, one translation unit per density kind (integrate_fast_*.cu)
-typedef int (*fast_launch_fn)(bool vegas, int ndim, const Dens& dens, const SampleArgs& a, unsigned blocks,
-                              int threads, size_t smem, cudaStream_t st);
-int launch_fast_camel(bool, int, const Dens&, const SampleArgs&, unsigned, int, size_t, cudaStream_t);
-int launch_fast_ucamel(bool, int, const Dens&, const SampleArgs&, unsigned, int, size_t, cudaStream_t);
-int launch_fast_banana(bool, int, const Dens&, const SampleArgs&, unsigned, int, size_t, cudaStream_t);
-int launch_fast_gaussian(bool, int, const Dens&, const SampleArgs&, unsigned, int, size_t, cudaStream_t);
-int launch_fast_uniform(bool, int, const Dens&, const SampleArgs&, unsigned, int, size_t, cudaStream_t);
+// `out`: per-point outputs (x, f, w, idx) requested -> the OUT instance of the same kernel
+int launch_fast_camel(bool vegas, bool out, int, const Dens&, const SampleArgs&, unsigned, int, size_t, cudaStream_t);
+int launch_fast_ucamel(bool vegas, bool out, int, const Dens&, const SampleArgs&, unsigned, int, size_t, cudaStream_t);
+int launch_fast_banana(bool vegas, bool out, int, const Dens&, const SampleArgs&, unsigned, int, size_t, cudaStream_t);
+int launch_fast_gaussian(bool vegas, bool out, int, const Dens&, const SampleArgs&, unsigned, int, size_t, cudaStream_t);
+int launch_fast_uniform(bool vegas, bool out, int, const Dens&, const SampleArgs&, unsigned, int, size_t, cudaStream_t);
+int launch_fast_none(bool vegas, bool out, int, const Dens&, const SampleArgs&, unsigned, int, size_t, cudaStream_t);
 
 #define HEPMC_DEFINE_FAST_LAUNCHER(NAME, KIND)                                                              \
-    int NAME(bool vegas, int ndim, const Dens& dens, const SampleArgs& a, unsigned blocks, int threads,     \
-             size_t smem, cudaStream_t st) {                                                                \
+    int NAME(bool vegas, bool out, int ndim, const Dens& dens, const SampleArgs& a, unsigned blocks,        \
+             int threads, size_t smem, cudaStream_t st) {                                                   \
         switch (ndim) {                                                                                     \
             HEPMC_FAST_CASE(KIND, 1) HEPMC_FAST_CASE(KIND, 2) HEPMC_FAST_CASE(KIND, 3) HEPMC_FAST_CASE(KIND, 4)     \
             HEPMC_FAST_CASE(KIND, 5) HEPMC_FAST_CASE(KIND, 6) HEPMC_FAST_CASE(KIND, 7) HEPMC_FAST_CASE(KIND, 8)     \
@@ -366,17 +391,23 @@ int launch_fast_uniform(bool, int, const Dens&, const SampleArgs&, unsigned, int
         }                                                                                                   \
         return 0;                                                                                           \
     }
+#define HEPMC_FAST_LAUNCH(KIND, ND, OUT)                                                                    \
+    do {                                                                                                    \
+        if (vegas) {                                                                                        \
+            HEPMC_CUDA(cudaFuncSetAttribute(vegas_sample_kernel<KIND, ND, true, OUT>,                       \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+            HEPMC_CUDA(cudaFuncSetAttribute(vegas_sample_kernel<KIND, ND, true, OUT>,                       \
+                                            cudaFuncAttributePreferredSharedMemoryCarveout, 100));          \
+            vegas_sample_kernel<KIND, ND, true, OUT><<<blocks, threads, smem, st>>>(dens, a);               \
+        } else {                                                                                            \
+            plain_sample_kernel<KIND, ND, true, OUT><<<blocks, 256, 0, st>>>(dens, a);                      \
+        }                                                                                                   \
+    } while (0)
 #define HEPMC_FAST_CASE(KIND, ND)                                                                           \
     case ND:                                                                                                \
-        if (vegas) {                                                                                        \
-            HEPMC_CUDA(cudaFuncSetAttribute(vegas_sample_kernel<KIND, ND, true>,                            \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-            HEPMC_CUDA(cudaFuncSetAttribute(vegas_sample_kernel<KIND, ND, true>,                            \
-                                            cudaFuncAttributePreferredSharedMemoryCarveout, 100));          \
-            vegas_sample_kernel<KIND, ND, true><<<blocks, threads, smem, st>>>(dens, a);                    \
-        } else {                                                                                            \
-            plain_sample_kernel<KIND, ND, true><<<blocks, 256, 0, st>>>(dens, a);                           \
-        }                                                                                                   \
+        if (out) HEPMC_FAST_LAUNCH(KIND, ND, true);                                                         \
+        else if (KIND != HEPMC_NONE) HEPMC_FAST_LAUNCH(KIND, ND, false);                                    \
+        else return -100;                                                                                   \
         break;
 
 }  // namespace hepmc
