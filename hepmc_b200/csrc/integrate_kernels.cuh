@@ -144,7 +144,7 @@ __device__ __forceinline__ SmemLayout carve(double* base, int ndim, int K, int n
 //       x / f / w / idx outputs are honoured through warp-uniform runtime flags.
 // Shared grid layout: per axis K entries of (bound_k, size_k) as double2 -> one LDS.128.
 template <int KIND, int NDIM_T, bool FAST, bool OUT = !FAST>
-__global__ void __launch_bounds__(256, (FAST && !OUT) ? kFastMinBlocks : (FAST ? 2 : 1)) vegas_sample_kernel(const __grid_constant__ Dens dens,
+__global__ void __launch_bounds__(256, FAST ? kFastMinBlocks : 1) vegas_sample_kernel(const __grid_constant__ Dens dens,
                                                            const __grid_constant__ SampleArgs a) {
     extern __shared__ double smem_raw[];
     const int ndim = NDIM_T ? NDIM_T : a.ndim;
