@@ -39,6 +39,10 @@ def call_integrand(fn, cols):
     if isinstance(fn, host_function):
         vals = fn(*[c.cpu().numpy() for c in cols])
     else:
+        if len(cols) > 1 and cols[0].stride(0) != 1:
+            # columns of a row-major (N, ndim) block: one transposing copy, then the integrand's
+            # elementwise ops run on contiguous arrays (several times faster than on stride-ndim views)
+            cols = list(torch.stack(cols, dim=0).unbind(0))
         try:
             vals = fn(*cols)
         except TypeError as exc:
