@@ -183,6 +183,8 @@ __global__ void __launch_bounds__(256, FAST ? kFastMinBlocks : 1) vegas_sample_k
     auto point = [&](int64_t li, double& wf, uint32_t (&packed)[NPACK]) {
         const uint64_t g = (uint64_t)(a.first_index + li);
         const bool ok = li < a.n;   // the FAST loop also runs the padding points of the last chunk: they store nothing
+        double* xp = (OUT && a.x_out && ok) ? a.x_out + li : nullptr;
+        int64_t* ip = (OUT && a.idx_out && ok) ? a.idx_out + li : nullptr;
         PdfAcc pa;
         pa.init();
         double w = 1.0;
@@ -214,8 +216,10 @@ __global__ void __launch_bounds__(256, FAST ? kFastMinBlocks : 1) vegas_sample_k
                             if (q == (d >> 2)) packed[q] |= bin << (8 * (d & 3));
                     }
                     if constexpr (OUT) {
-                        if (a.x_out && ok) a.x_out[(int64_t)d * a.n + li] = x;
-                        if (a.idx_out && ok) a.idx_out[(int64_t)d * a.n + li] = (int64_t)bin;
+                        // dim-major outputs: running pointers (one 64-bit add per axis instead of a
+                        // 64-bit multiply-add per store)
+                        if (xp) { *xp = x; xp += a.n; }
+                        if (ip) { *ip = (int64_t)bin; ip += a.n; }
                     }
                 }
             }
