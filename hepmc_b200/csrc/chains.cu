@@ -5,6 +5,7 @@
 // State (x, pdf, counters) lives in registers; randomness is Philox4x32-10 keyed by the
 // GLOBAL chain index and the step, so any split of the chain range over GPUs reproduces
 // the same chains.  Acceptance counts: per chain + warp-shuffle reduced grid total.
+#include <stdlib.h>
 #include "chains.cuh"
 
 namespace hepmc {
@@ -96,20 +97,63 @@ __global__ void __launch_bounds__(128) rwm_kernel(const __grid_constant__ Dens d
 
 // ------------------------------------------------------------------ HMC
 // hmc.py:54-88, simulation.py:34-42.  pdist = Gaussian(0, diag(mass)) as a Dens block.
-template <int NDIM, class T>
+// COOP = true (small ensembles with a surrogate gradient): ONE CTA per chain.  Every thread carries
+// the chain state redundantly (bit-identical: same draws, same arithmetic); the node sum of each
+// gradient is split over the 128 threads and added up in a fixed order, so one chain no longer
+// walks its 1024 nodes in a single thread.  Thread 0 writes the outputs.
+constexpr int kCoopThreads = 128;
+
+template <int NDIM>
+__device__ __forceinline__ void coop_sum(double (&g)[NDIM], double* red) {
+#pragma unroll
+    for (int k = 0; k < NDIM; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) g[k] += __shfl_xor_sync(0xffffffffu, g[k], o);
+    }
+    const int warp = threadIdx.x >> 5;
+    __syncthreads();   // previous sum has been read
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < NDIM; ++k) red[warp * NDIM + k] = g[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NDIM; ++k) {
+        double r = red[k];
+#pragma unroll
+        for (int w = 1; w < kCoopThreads / 32; ++w) r += red[w * NDIM + k];
+        g[k] = r;
+    }
+}
+
+template <int NDIM, class T, bool COOP = false>
 __global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ Dens dens,
                                                   const __grid_constant__ Dens pdist,
                                                   const __grid_constant__ hepmc_elm_t elm,
                                                   const __grid_constant__ ChainArgs a, int tab_in_smem) {
     extern __shared__ double smem_raw[];
+    __shared__ double s_red[COOP ? (kCoopThreads / 32) * NDIM : 1];
     T* tab = reinterpret_cast<T*>(smem_raw);
     const bool use_elm = elm.mode != HEPMC_GRAD_EXACT;
     if (use_elm && tab_in_smem) {
         elm_stage_tables<T>(elm, NDIM, tab);
         __syncthreads();
     }
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t c = COOP ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = c < a.n_chains;
+    const bool writer = !COOP || threadIdx.x == 0;
+    auto gradient = [&](const double (&q)[NDIM], double (&grad)[NDIM]) {
+        if (use_elm) {
+            if constexpr (COOP) {
+                elm_gradient<NDIM, T>(elm.mode, elm.nodes, tab, q, grad, (int)threadIdx.x, kCoopThreads);
+                coop_sum<NDIM>(grad, s_red);
+            } else {
+                elm_gradient<NDIM, T>(elm.mode, elm.nodes, tab, q, grad);
+            }
+        } else {
+            density_pot_gradient_n<NDIM>(dens, q, grad);
+        }
+    };
     const PhiloxKey key = philox_expand(a.seed);
     constexpr int NCALL = (NDIM + 1) / 2;
     constexpr uint32_t CPS = NCALL + 1;
@@ -121,7 +165,7 @@ __global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ Dens d
 #pragma unroll
         for (int d = 0; d < NDIM; ++d) x[d] = a.x0[c * NDIM + d];
         double pdf = density_pdf_n<NDIM>(dens, x);
-        if (a.chain) store_state<NDIM>(a.chain, c, a.n_kept, 0, x);
+        if (a.chain && writer) store_state<NDIM>(a.chain, c, a.n_kept, 0, x);
         for (int64_t t = 1; t < a.T; ++t) {
             double p0[NDIM], q[NDIM], p[NDIM], grad[NDIM];
             if (a.z_replay) {
@@ -142,15 +186,13 @@ __global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ Dens d
 #pragma unroll
             for (int d = 0; d < NDIM; ++d) { q[d] = x[d]; p[d] = p0[d]; }
             // leapfrog, simulation.py:36-42
-            if (use_elm) elm_gradient<NDIM, T>(elm.mode, elm.nodes, tab, q, grad);
-            else density_pot_gradient_n<NDIM>(dens, q, grad);
+            gradient(q, grad);
             for (int s = 0; s < a.steps; ++s) {
 #pragma unroll
                 for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
 #pragma unroll
                 for (int d = 0; d < NDIM; ++d) q[d] += a.step_size * (pdist.c[d] * (p[d] - pdist.a[d]));
-                if (use_elm) elm_gradient<NDIM, T>(elm.mode, elm.nodes, tab, q, grad);
-                else density_pot_gradient_n<NDIM>(dens, q, grad);
+                gradient(q, grad);
 #pragma unroll
                 for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
             }
@@ -177,14 +219,30 @@ __global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ Dens d
                 pdf = cpdf;
                 acc += changed ? 1 : 0;
             }
-            if (a.chain && (t % a.thin) == 0) store_state<NDIM>(a.chain, c, a.n_kept, t / a.thin, x);
+            if (a.chain && writer && (t % a.thin) == 0) store_state<NDIM>(a.chain, c, a.n_kept, t / a.thin, x);
         }
-        if (a.last) {
+        if (a.last && writer) {
 #pragma unroll
             for (int d = 0; d < NDIM; ++d) a.last[c * NDIM + d] = x[d];
         }
     }
-    finish_counts(a, active, c, acc);
+    finish_counts(a, active && writer, c, acc);
+}
+
+// Ensembles up to this many chains per call run the cooperative HMC kernel.  Measured crossover of
+// the total throughput (scripts/coop_perf.py, camel-8D, 20 leapfrog): ~12 000 chains at 1024 nodes,
+// ~2000-3700 at 100 nodes; below it the cooperative kernel is up to 48x faster per chain
+// (one chain, 1024 nodes, float64: 2.3e4 instead of 4.8e2 steps/s).  Development override:
+// HEPMC_HMC_COOP_MAX.
+static int64_t coop_max_chains(int nodes) {
+    static int64_t forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("HEPMC_HMC_COOP_MAX");
+        forced = e ? atoll(e) : -1;
+    }
+    if (forced >= 0) return forced;
+    const int64_t v = 8 * (int64_t)nodes;
+    return v < 1024 ? 1024 : (v > 8192 ? 8192 : v);
 }
 
 static int fill_chain_args(ChainArgs& a, const char* who, int ndim, const double* x0_dev, const double* scale_host,
@@ -308,18 +366,27 @@ int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int pr
     size_t smem = el.mode == HEPMC_GRAD_EXACT ? 0 : (size_t)el.nodes * elm_row(nd) * esz;
     HEPMC_REQUIRE(smem <= (size_t)maxs, HEPMC_E_UNSUPPORTED,
                   "hepmc_hmc_chains: %d surrogate nodes do not fit shared memory (%zu > %d bytes)", el.nodes, smem, maxs);
+    // small ensembles with a surrogate gradient: one CTA per chain (see hmc_kernel<.., COOP>); the
+    // threshold is a property of the CALL (its local chain count), results of the two kernels differ
+    // in the last bits of the gradient sums
+    const bool coop = el.mode != HEPMC_GRAD_EXACT && n_chains <= coop_max_chains(el.nodes);
+    const unsigned cblocks = (unsigned)n_chains;
+#define HMC_LAUNCH(ND, TT, CO, NB)                                                                         \
+    do {                                                                                                   \
+        HEPMC_CUDA(cudaFuncSetAttribute(hmc_kernel<ND, TT, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        hmc_kernel<ND, TT, CO><<<NB, threads, smem, st>>>(*dens, pd, el, a, 1);                            \
+    } while (0)
 #define HMC_CASE(ND)                                                                                       \
     do {                                                                                                   \
         if (precision == 0) {                                                                              \
-            HEPMC_CUDA(cudaFuncSetAttribute(hmc_kernel<ND, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            hmc_kernel<ND, double><<<blocks, threads, smem, st>>>(*dens, pd, el, a, 1);                    \
+            if (coop) HMC_LAUNCH(ND, double, true, cblocks); else HMC_LAUNCH(ND, double, false, blocks);   \
         } else {                                                                                           \
-            HEPMC_CUDA(cudaFuncSetAttribute(hmc_kernel<ND, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-            hmc_kernel<ND, float><<<blocks, threads, smem, st>>>(*dens, pd, el, a, 1);                     \
+            if (coop) HMC_LAUNCH(ND, float, true, cblocks); else HMC_LAUNCH(ND, float, false, blocks);     \
         }                                                                                                  \
     } while (0)
     HEPMC_DISPATCH_NDIM(nd, HMC_CASE);
 #undef HMC_CASE
+#undef HMC_LAUNCH
     HEPMC_LAUNCH_CHECK();
     return 0;
 }

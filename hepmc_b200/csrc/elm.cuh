@@ -36,9 +36,11 @@ __device__ __forceinline__ void elm_sincos(double x, double* s, double* c) { sin
 __device__ __forceinline__ void elm_sincos(float x, float* s, float* c) { __sincosf(x, s, c); }
 
 // gradient of the surrogate at x -> g (both double, NDIM compile-time)
+// `first`, `stride`: this thread's share of the nodes (cooperative kernels: thread t of S takes
+// nodes t, t + S, ...; the caller sums the partial gradients)
 template <int NDIM, class T>
 __device__ __forceinline__ void elm_gradient(int mode, int nodes, const T* __restrict__ tab,
-                                             const double (&x)[NDIM], double (&g)[NDIM]) {
+                                             const double (&x)[NDIM], double (&g)[NDIM], int first = 0, int stride = 1) {
     constexpr int row = NDIM + 3;
     T xt[NDIM], acc[NDIM];
 #pragma unroll
@@ -63,12 +65,12 @@ __device__ __forceinline__ void elm_gradient(int mode, int nodes, const T* __res
             // float64: two nodes in flight and split square sums (the FP64 pipe is latency bound
             // at the occupancy 168 registers allow)
 #pragma unroll 2
-            for (int i = 0; i < nodes; ++i) node(i);
+            for (int i = first; i < nodes; i += stride) node(i);
         } else {
-            for (int i = 0; i < nodes; ++i) node(i);  // float32: compiler's own unrolling (issue bound)
+            for (int i = first; i < nodes; i += stride) node(i);  // float32: compiler's own unrolling (issue bound)
         }
     } else {
-        for (int i = 0; i < nodes; ++i) {
+        for (int i = first; i < nodes; i += stride) {
             const T* r = tab + i * row;
             T in = r[NDIM];
 #pragma unroll

@@ -755,6 +755,30 @@ def test_elm_gradient_tc32_mode():
             assert np.all(np.abs(g3 - g64) <= 2e-5 * scale + 1e-30), (nodes, ndim, J, float(np.max(np.abs(g3 - g64) / (scale + 1e-300))))
 
 
+def test_hmc_cooperative_kernel_matches_thread_per_chain():
+    """Small ensembles with a surrogate gradient run one CTA per chain (node sum split over 128
+    threads); the same chains inside a large ensemble run one thread per chain.  Same draws (global
+    chain indices), same trajectories up to the summation order of the gradient."""
+    e, params, bias, w = _elm("g100")
+    rs = np.random.default_rng(12)
+    big = 1 / 3 + 0.05 * rs.standard_normal((3000, 8))          # > 8 * 100 nodes (min 1024): thread per chain
+    for prec, tol in (("f64", 1e-9), ("f32", 2e-3)):
+        out = []
+        for x0 in (big[:5], big):
+            H.seed(4242)
+            tgt = H.densities.Camel(8)
+            H.surrogate.attach_surrogate_gradient(tgt, H.surrogate.GaussianBasis(8), params, bias, w)
+            upd = H.hamiltonian.HamiltonianUpdate(tgt, H.densities.Gaussian(8), 10, 0.02, precision=prec)
+            out.append(upd.sample(15, x0))
+        small, large = out
+        assert np.array_equal(small.accepted, large.accepted[:5]), prec
+        assert_close(small.data, large.data[:5], tol, atol=tol)
+    # a single chain keeps the reference's (T, ndim) shape on the cooperative kernel
+    H.seed(4242)
+    one = upd.sample(15, big[0])
+    assert one.data.shape == (15, 8) and np.allclose(one.data, out[0].data[0], rtol=2e-3, atol=2e-3)
+
+
 def test_hmc_tensor_core_surrogate_is_an_exact_sampler():
     H.seed(99)
     ndim, C, T = 8, 2000, 30
