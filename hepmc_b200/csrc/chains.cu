@@ -97,35 +97,6 @@ __global__ void __launch_bounds__(128) rwm_kernel(const __grid_constant__ Dens d
 
 // ------------------------------------------------------------------ HMC
 // hmc.py:54-88, simulation.py:34-42.  pdist = Gaussian(0, diag(mass)) as a Dens block.
-// COOP = true (small ensembles with a surrogate gradient): ONE CTA per chain.  Every thread carries
-// the chain state redundantly (bit-identical: same draws, same arithmetic); the node sum of each
-// gradient is split over the 128 threads and added up in a fixed order, so one chain no longer
-// walks its 1024 nodes in a single thread.  Thread 0 writes the outputs.
-constexpr int kCoopThreads = 128;
-
-template <int NDIM>
-__device__ __forceinline__ void coop_sum(double (&g)[NDIM], double* red) {
-#pragma unroll
-    for (int k = 0; k < NDIM; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) g[k] += __shfl_xor_sync(0xffffffffu, g[k], o);
-    }
-    const int warp = threadIdx.x >> 5;
-    __syncthreads();   // previous sum has been read
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int k = 0; k < NDIM; ++k) red[warp * NDIM + k] = g[k];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < NDIM; ++k) {
-        double r = red[k];
-#pragma unroll
-        for (int w = 1; w < kCoopThreads / 32; ++w) r += red[w * NDIM + k];
-        g[k] = r;
-    }
-}
-
 template <int NDIM, class T, bool COOP = false>
 __global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ Dens dens,
                                                   const __grid_constant__ Dens pdist,
@@ -227,22 +198,6 @@ __global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ Dens d
         }
     }
     finish_counts(a, active && writer, c, acc);
-}
-
-// Ensembles up to this many chains per call run the cooperative HMC kernel.  Measured crossover of
-// the total throughput (scripts/coop_perf.py, camel-8D, 20 leapfrog): ~12 000 chains at 1024 nodes,
-// ~2000-3700 at 100 nodes; below it the cooperative kernel is up to 48x faster per chain
-// (one chain, 1024 nodes, float64: 2.3e4 instead of 4.8e2 steps/s).  Development override:
-// HEPMC_HMC_COOP_MAX.
-static int64_t coop_max_chains(int nodes) {
-    static int64_t forced = -2;
-    if (forced == -2) {
-        const char* e = getenv("HEPMC_HMC_COOP_MAX");
-        forced = e ? atoll(e) : -1;
-    }
-    if (forced >= 0) return forced;
-    const int64_t v = 8 * (int64_t)nodes;
-    return v < 1024 ? 1024 : (v > 8192 ? 8192 : v);
 }
 
 static int fill_chain_args(ChainArgs& a, const char* who, int ndim, const double* x0_dev, const double* scale_host,

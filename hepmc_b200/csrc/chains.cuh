@@ -1,6 +1,7 @@
 // Shared pieces of the chain-ensemble kernels (chains.cu: SIMT kernels; elm_tc.cu: HMC with the
 // ELM gradient on tensor cores).
 #pragma once
+#include <stdlib.h>
 #include "density.cuh"
 #include "elm.cuh"
 
@@ -50,6 +51,51 @@ __device__ __forceinline__ void finish_counts(const ChainArgs& a, bool active, i
     if ((threadIdx.x & 31) == 0 && a.total_accepted && tot) atomicAdd(a.total_accepted, (unsigned long long)tot);
 }
 
+
+// COOP = true (small ensembles with a surrogate gradient): ONE CTA per chain.  Every thread carries
+// the chain state redundantly (bit-identical: same draws, same arithmetic); the node sum of each
+// gradient is split over the 128 threads and added up in a fixed order, so one chain no longer
+// walks its 1024 nodes in a single thread.  Thread 0 writes the outputs.
+constexpr int kCoopThreads = 128;
+
+template <int NDIM>
+__device__ __forceinline__ void coop_sum(double (&g)[NDIM], double* red) {
+#pragma unroll
+    for (int k = 0; k < NDIM; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) g[k] += __shfl_xor_sync(0xffffffffu, g[k], o);
+    }
+    const int warp = threadIdx.x >> 5;
+    __syncthreads();   // previous sum has been read
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < NDIM; ++k) red[warp * NDIM + k] = g[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NDIM; ++k) {
+        double r = red[k];
+#pragma unroll
+        for (int w = 1; w < kCoopThreads / 32; ++w) r += red[w * NDIM + k];
+        g[k] = r;
+    }
+}
+
+// Ensembles up to this many chains per call run the cooperative HMC kernel.  Measured crossover of
+// the total throughput (scripts/coop_perf.py, camel-8D, 20 leapfrog): ~12 000 chains at 1024 nodes,
+// ~2000-3700 at 100 nodes; below it the cooperative kernel is up to 48x faster per chain
+// (one chain, 1024 nodes, float64: 2.3e4 instead of 4.8e2 steps/s).  Development override:
+// HEPMC_HMC_COOP_MAX.
+inline int64_t coop_max_chains(int nodes) {
+    static int64_t forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("HEPMC_HMC_COOP_MAX");
+        forced = e ? atoll(e) : -1;
+    }
+    if (forced >= 0) return forced;
+    const int64_t v = 8 * (int64_t)nodes;
+    return v < 1024 ? 1024 : (v > 8192 ? 8192 : v);
+}
 
 // tensor-core launchers (elm_tc.cu)
 int launch_hmc_tc(const Dens& dens, const Dens& pdist, const hepmc_elm_t& elm, const ChainArgs& a, bool fma_g2,

@@ -42,20 +42,36 @@ __device__ __forceinline__ double mixture_pdf(const double* tab, int nch, int nd
     return p;
 }
 
-template <int NDIM, class T>
+template <int NDIM, class T, bool COOP = false>
 __global__ void __launch_bounds__(128) mc3_kernel(const __grid_constant__ Dens dens, const __grid_constant__ Dens pdist,
                                                   const __grid_constant__ hepmc_elm_t elm,
                                                   const __grid_constant__ ChainArgs a,
                                                   const __grid_constant__ Mc3Args m) {
     extern __shared__ double smem_raw[];
+    __shared__ double s_red[COOP ? (kCoopThreads / 32) * NDIM : 1];
     double* s_tab = smem_raw;  // channel table
     T* tab = reinterpret_cast<T*>(s_tab + m.nch * kMcRow);  // ELM node table
     for (int i = threadIdx.x; i < m.nch * kMcRow; i += blockDim.x) s_tab[i] = m.table[i];
     const bool use_elm = elm.mode != HEPMC_GRAD_EXACT;
     if (use_elm && m.local_kind == 1) elm_stage_tables<T>(elm, NDIM, tab);
     __syncthreads();
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // COOP: one CTA per chain, all threads carry the chain redundantly, the surrogate's node sum is
+    // split over the threads (see hmc_kernel in chains.cu)
+    const int64_t c = COOP ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = c < a.n_chains;
+    const bool writer = !COOP || threadIdx.x == 0;
+    auto gradient = [&](const double (&q)[NDIM], double (&grad)[NDIM]) {
+        if (use_elm) {
+            if constexpr (COOP) {
+                elm_gradient<NDIM, T>(elm.mode, elm.nodes, tab, q, grad, (int)threadIdx.x, kCoopThreads);
+                coop_sum<NDIM>(grad, s_red);
+            } else {
+                elm_gradient<NDIM, T>(elm.mode, elm.nodes, tab, q, grad);
+            }
+        } else {
+            density_pot_gradient_n<NDIM>(dens, q, grad);
+        }
+    };
     const PhiloxKey key = philox_expand(a.seed);
     constexpr int NCALL = (NDIM + 1) / 2;
     constexpr uint32_t CPS = NCALL + 2;  // [selector + channel pick | NCALL sample draws | accept uniform]
@@ -67,7 +83,7 @@ __global__ void __launch_bounds__(128) mc3_kernel(const __grid_constant__ Dens d
 #pragma unroll
         for (int d = 0; d < NDIM; ++d) x[d] = a.x0[c * NDIM + d];
         double pdf = density_pdf_n<NDIM>(dens, x);
-        if (a.chain) store_state<NDIM>(a.chain, c, a.n_kept, 0, x);
+        if (a.chain && writer) store_state<NDIM>(a.chain, c, a.n_kept, 0, x);
         for (int64_t t = 1; t < a.T; ++t) {
             const uint32_t base = (uint32_t)(t - 1) * CPS;
             const size_t tape = (size_t)c * (a.T - 1) + (t - 1);
@@ -172,15 +188,13 @@ __global__ void __launch_bounds__(128) mc3_kernel(const __grid_constant__ Dens d
                 }
 #pragma unroll
                 for (int d = 0; d < NDIM; ++d) { cand[d] = x[d]; p[d] = p0[d]; }
-                if (use_elm) elm_gradient<NDIM, T>(elm.mode, elm.nodes, tab, cand, grad);
-                else density_pot_gradient_n<NDIM>(dens, cand, grad);
+                gradient(cand, grad);
                 for (int s = 0; s < a.steps; ++s) {
 #pragma unroll
                     for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
 #pragma unroll
                     for (int d = 0; d < NDIM; ++d) cand[d] += a.step_size * (pdist.c[d] * (p[d] - pdist.a[d]));
-                    if (use_elm) elm_gradient<NDIM, T>(elm.mode, elm.nodes, tab, cand, grad);
-                    else density_pot_gradient_n<NDIM>(dens, cand, grad);
+                    gradient(cand, grad);
 #pragma unroll
                     for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
                 }
@@ -205,14 +219,14 @@ __global__ void __launch_bounds__(128) mc3_kernel(const __grid_constant__ Dens d
                 pdf = cpdf;
                 acc += changed ? 1 : 0;
             }
-            if (a.chain && (t % a.thin) == 0) store_state<NDIM>(a.chain, c, a.n_kept, t / a.thin, x);
+            if (a.chain && writer && (t % a.thin) == 0) store_state<NDIM>(a.chain, c, a.n_kept, t / a.thin, x);
         }
-        if (a.last) {
+        if (a.last && writer) {
 #pragma unroll
             for (int d = 0; d < NDIM; ++d) a.last[c * NDIM + d] = x[d];
         }
     }
-    finish_counts(a, active, c, acc);
+    finish_counts(a, active && writer, c, acc);
 }
 
 }  // namespace hepmc
@@ -284,20 +298,25 @@ extern "C" int hepmc_mc3_chains(const hepmc_density_t* dens, const double* chann
     const size_t esz = precision == 0 ? 8 : 4;
     size_t smem = (size_t)n_channels * kMcRow * 8 + (el.mode == HEPMC_GRAD_EXACT ? 0 : (size_t)el.nodes * elm_row(nd) * esz);
     HEPMC_REQUIRE(smem <= (size_t)maxs, HEPMC_E_UNSUPPORTED, "hepmc_mc3_chains: tables need %zu bytes of shared memory", smem);
-    const unsigned blocks = (unsigned)((n_chains + 127) / 128);
+    const bool coop = el.mode != HEPMC_GRAD_EXACT && n_chains <= coop_max_chains(el.nodes);
+    const unsigned blocks = coop ? (unsigned)n_chains : (unsigned)((n_chains + 127) / 128);
     cudaStream_t st = as_stream(stream);
+#define MC3_LAUNCH(ND, TT, CO)                                                                                  \
+    do {                                                                                                        \
+        HEPMC_CUDA(cudaFuncSetAttribute(mc3_kernel<ND, TT, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        mc3_kernel<ND, TT, CO><<<blocks, 128, smem, st>>>(*dens, pd, el, a, m);                                 \
+    } while (0)
 #define MC3_CASE(ND)                                                                                            \
     do {                                                                                                        \
         if (precision == 0) {                                                                                   \
-            HEPMC_CUDA(cudaFuncSetAttribute(mc3_kernel<ND, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            mc3_kernel<ND, double><<<blocks, 128, smem, st>>>(*dens, pd, el, a, m);                             \
+            if (coop) MC3_LAUNCH(ND, double, true); else MC3_LAUNCH(ND, double, false);                         \
         } else {                                                                                                \
-            HEPMC_CUDA(cudaFuncSetAttribute(mc3_kernel<ND, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-            mc3_kernel<ND, float><<<blocks, 128, smem, st>>>(*dens, pd, el, a, m);                              \
+            if (coop) MC3_LAUNCH(ND, float, true); else MC3_LAUNCH(ND, float, false);                           \
         }                                                                                                       \
     } while (0)
     HEPMC_DISPATCH_NDIM(nd, MC3_CASE);
 #undef MC3_CASE
+#undef MC3_LAUNCH
     HEPMC_LAUNCH_CHECK();
     return 0;
 }

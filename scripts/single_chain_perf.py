@@ -30,3 +30,11 @@ for C in chains:
             upd = H.hamiltonian.HamiltonianUpdate(tgt, H.densities.Gaussian(8), 20, 0.01, precision=prec)
             T = 201 if (nodes == 1024 and prec in ("f64", "f32")) else 1001
             print("C %5d HMC camel-8D ELM %4d %-5s    : %.3e steps/s per chain" % (C, nodes, prec, rate(upd, T, x8)))
+
+# the reference's recipe (interfaces/mc3_hmc_el.py): mixing of IS-Metropolis and surrogate HMC, one chain
+for el_size in (100, 1024):
+    H.seed(1)
+    target = H.densities.Camel(8)
+    sampler, initial = H.interfaces.mc3_hmc_el.get_sampler(target, 8, 0.4, [1 / 3, 2 / 3], [0.1, 0.1], 0.5, nintegral=4000,
+                                                           mass=1., steps=20, step_size=0.01, el_size=el_size)
+    print("C     1 mc3_hmc_el recipe, el_size %4d  : %.3e steps/s per chain" % (el_size, rate(sampler, 2001, initial)))
