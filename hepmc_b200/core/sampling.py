@@ -47,29 +47,36 @@ class Sample(object):
 
     @property
     def size(self):
+        """Number of states per chain: data.shape[0] like the reference; for an ensemble
+        (C, T, ndim) the chain length T."""
         try:
-            return self.data.shape[0]
+            return self.data.shape[-2] if len(self.data.shape) == 3 else self.data.shape[0]
         except AttributeError:
             return None
 
     @property
     def ndim(self):
         try:
-            return self.data.shape[1]
+            return self.data.shape[-1] if len(self.data.shape) == 3 else self.data.shape[1]
         except AttributeError:
             return None
+
+    def _states(self):
+        """All states as one (N, ndim) array (an ensemble is pooled)."""
+        d = self.data
+        return d.reshape(-1, d.shape[-1]) if len(d.shape) == 3 else d
 
     @property
     def mean(self):
         if self._mean is None and _set(self.data):
-            d = self.data
+            d = self._states()
             self._mean = d.mean(dim=0) if isinstance(d, torch.Tensor) else np.mean(d, axis=0)
         return self._mean
 
     @property
     def variance(self):
         if self._variance is None and _set(self.data):
-            d = self.data
+            d = self._states()
             self._variance = d.var(dim=0, unbiased=False) if isinstance(d, torch.Tensor) else np.var(d, axis=0)
         return self._variance
 

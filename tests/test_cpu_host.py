@@ -185,3 +185,18 @@ def test_interfaces_namespace():
     assert list(inspect.signature(H.interfaces.mc3_gauss.get_sampler).parameters)[-1] == "local_width"
     with pytest.raises(NotImplementedError):
         H.interfaces.plain_nuts.get_sampler(None, 2, 0.5)
+
+
+def test_sample_summaries_single_chain_and_ensemble():
+    """Sample.size / ndim / mean / variance: the reference's meaning for (T, ndim) data; an ensemble
+    (C, T, ndim) reports the chain length and pools the states."""
+    import hepmc_b200 as H
+    rs = np.random.RandomState(0)
+    one = H.core.sampling.Sample(data=rs.rand(50, 3))
+    assert (one.size, one.ndim) == (50, 3)
+    assert np.allclose(one.mean, one.data.mean(axis=0)) and np.allclose(one.variance, one.data.var(axis=0))
+    ens = H.core.sampling.Sample(data=rs.rand(7, 50, 3))
+    assert (ens.size, ens.ndim) == (50, 3)
+    assert np.allclose(ens.mean, ens.data.reshape(-1, 3).mean(axis=0))
+    assert np.allclose(ens.variance, ens.data.reshape(-1, 3).var(axis=0))
+    assert H.core.sampling.Sample().size is None and "N/A" in repr(H.core.sampling.Sample())

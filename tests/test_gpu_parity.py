@@ -1009,3 +1009,23 @@ def test_interfaces_recipes():
             assert np.all(res[:, 0] < 1.5 * res[:, 1]), (name, res)   # 8 KS checks at alpha = 0.05: some slack
     with pytest.raises(NotImplementedError):
         H.interfaces.mc3_nuts.get_sampler(H.densities.Camel(2), 2, 0.4, centers, widths, 0.5)
+
+
+def test_sample_repr_for_an_ensemble():
+    """Sample.__repr__ of an ensemble: pooled bin-wise chi^2, per-chain effective sample sizes."""
+    H.seed(8)
+    tgt = H.densities.Camel(2)
+    met = H.DefaultMetropolis(2, tgt, H.proposals.Gaussian(2, cov=0.02 * np.eye(2)))
+    x0 = np.tile([0.35, 0.3], (64, 1))
+    x0[32:] = [0.65, 0.7]
+    s = met.sample(2000, x0)
+    assert (s.size, s.ndim) == (2000, 2)
+    ess = s.effective_sample_size
+    assert ess.shape == (64, 2) and np.all(ess > 1) and np.all(ess <= 2000)
+    red, p, n = s.bin_wise_chi2
+    assert n > 20 and red > 0
+    text = repr(s)
+    assert "effective sample size" in text and "bin-wise chi^2: %.4g" % red in text
+    # one chain of the ensemble analysed alone gives the same effective sample size
+    from hepmc_b200.core.util import stat_tools
+    assert np.array_equal(stat_tools.effective_sample_size(s.data[5], tgt.mean, tgt.variance), ess[5])
