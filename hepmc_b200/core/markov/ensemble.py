@@ -95,3 +95,129 @@ def run_hmc(blk, elm_blk, precision, x0, mass_diag, step_size, steps, sample_siz
               _lib.ptr(p), _lib.ptr(u), _lib.ptr(chain), _lib.ptr(last), _lib.ptr(accepted), _lib.ptr(total),
               _lib.stream_ptr())
     return chain, last, accepted, total
+
+
+# ---------------------------------------------------------------------------------------------
+# Generic path: targets that are NOT built-in densities (user classes / callables).  The chain
+# kernels cannot call Python, so -- like the integrators' two-kernel path for user integrands --
+# every step is: draws from the native generator (one kernel, Philox counter = global chain
+# index, one stream id per step) -> proposal arithmetic -> the USER's pdf / pot_gradient on the
+# (C, ndim) CUDA tensor -> accept / reject, all on the device, vectorised over the ensemble.
+# Cost is a few dozen launches per step whatever the ensemble size: for one chain this is on par
+# with the reference, for 1e5 chains it is 1e5 times that.  No host arithmetic, no CPU fallback.
+# ---------------------------------------------------------------------------------------------
+def _user_values(fn, x, what):
+    """fn(x) for x (C, ndim) on the device -> float64 CUDA tensor; fn may answer with a tensor or
+    anything np.asarray understands (util.host_function marks NumPy code: it gets a host copy)."""
+    from ..util.helper import host_function
+    if isinstance(fn, host_function):
+        out = fn(x.cpu().numpy())
+    else:
+        try:
+            out = fn(x)
+        except TypeError as exc:
+            raise TypeError("the target's %s failed on a CUDA tensor (%s).  User-defined targets of chain updates "
+                            "must accept torch CUDA tensors of shape (C, ndim), or be wrapped in "
+                            "hepmc_b200.util.host_function." % (what, exc)) from exc
+    if not isinstance(out, torch.Tensor):
+        out = torch.as_tensor(np.asarray(out, dtype=np.float64))
+    return out.to(device=x.device, dtype=torch.float64)
+
+
+def _step_draws(n_chains, n_uniform, first_chain, stream_id, dev):
+    """(C, n_uniform) uniforms of one step; chain c uses counter first_chain + c."""
+    from ..integration.engine import none_block
+    out = torch.empty((n_chains, n_uniform), dtype=torch.float64, device=dev)
+    blk = none_block(n_uniform)
+    _lib.call("hepmc_plain_mc_sample", ctypes.byref(blk), n_chains, int(first_chain), _lib.default_chunk(n_chains),
+              rng.get_seed(), int(stream_id), None, _lib.ptr(out), None, None, _lib.stream_ptr())
+    return out
+
+
+def _normals(u, ndim):
+    """Box-Muller on column pairs of u -> (C, ndim) standard normals."""
+    npair = (ndim + 1) // 2
+    r = torch.sqrt(-2.0 * torch.log(u[:, 0:2 * npair:2]))
+    ang = 2.0 * np.pi * u[:, 1:2 * npair:2]
+    return torch.stack((r * torch.cos(ang), r * torch.sin(ang)), dim=2).reshape(u.shape[0], 2 * npair)[:, :ndim]
+
+
+def _metropolis_accept(state, pdf, cand, cpdf, prob, u, accepted):
+    take = (prob >= 1) | (u < prob)                       # metropolis.py:87; NaN -> reject
+    changed = take & (cand != state).any(dim=1)           # base.py:72-73
+    accepted += changed.to(torch.int64)
+    return torch.where(take[:, None], cand, state), torch.where(take, cpdf, pdf)
+
+
+def run_rwm_generic(pdf_fn, x0, proposal_kind, prop_param, sample_size, thin=1, store_chain=True, first_chain=0):
+    """DefaultMetropolis over a user-defined target (symmetric proposals: kinds 0, 1, 2 of
+    hepmc_rwm_chains)."""
+    dev = x0.device
+    C, ndim = x0.shape
+    chain, last, accepted, total = alloc_outputs(C, ndim, sample_size, thin, store_chain, dev)
+    par = torch.as_tensor(np.array(prop_param, dtype=np.float64), device=dev)
+    npair = (ndim + 1) // 2
+    n_draw = 2 * npair if proposal_kind == 0 else (ndim if proposal_kind == 1 else 1)
+    sid0 = rng.next_stream(max(sample_size - 1, 1))
+    state = x0.clone()
+    pdf = _user_values(pdf_fn, state, "pdf").reshape(C)
+    if chain is not None:
+        chain[:, 0] = state
+    for t in range(1, sample_size):
+        u = _step_draws(C, n_draw + 1, first_chain, sid0 + t - 1, dev)
+        if proposal_kind == 0:
+            cand = state + par[:ndim] * _normals(u, ndim)
+        elif proposal_kind == 1:
+            cand = par[0] + (par[1] - par[0]) * u[:, :ndim]
+        else:
+            delta, lo, hi = par[:ndim], par[ndim], par[ndim + 1]
+            cand = torch.minimum(torch.clamp(state - delta / 2, min=float(lo)), hi - delta) + u[:, :1] * delta
+        cpdf = _user_values(pdf_fn, cand, "pdf").reshape(C)
+        state, pdf = _metropolis_accept(state, pdf, cand, cpdf, cpdf / pdf, u[:, -1], accepted)
+        if chain is not None and t % thin == 0:
+            chain[:, t // thin] = state
+    last.copy_(state)
+    total += accepted.sum()
+    return chain, last, accepted, total
+
+
+def run_hmc_generic(pdf_fn, grad_fn, x0, mass_diag, step_size, steps, sample_size, thin=1, store_chain=True,
+                    first_chain=0):
+    """HamiltonianUpdate over a user-defined target: leapfrog of simulation.py:34-42 with the user's
+    pot_gradient, momentum ~ N(0, diag(mass)), acceptance of hmc.py:54-59."""
+    dev = x0.device
+    C, ndim = x0.shape
+    chain, last, accepted, total = alloc_outputs(C, ndim, sample_size, thin, store_chain, dev)
+    mass = torch.as_tensor(np.array(mass_diag, dtype=np.float64), device=dev)
+    npair = (ndim + 1) // 2
+    sid0 = rng.next_stream(max(sample_size - 1, 1))
+    state = x0.clone()
+    pdf = _user_values(pdf_fn, state, "pdf").reshape(C)
+    if chain is not None:
+        chain[:, 0] = state
+    half = step_size / 2
+
+    def grad(q):
+        return _user_values(grad_fn, q, "pot_gradient").reshape(C, ndim)
+
+    for t in range(1, sample_size):
+        u = _step_draws(C, 2 * npair + 1, first_chain, sid0 + t - 1, dev)
+        p0 = torch.sqrt(mass) * _normals(u, ndim)
+        q, p = state.clone(), p0.clone()
+        g = grad(q)
+        for _ in range(int(steps)):
+            p = p - half * g
+            q = q + step_size * (p / mass)
+            g = grad(q)
+            p = p - half * g
+        cpdf = _user_values(pdf_fn, q, "pdf").reshape(C)
+        # N(p) / N(p0) for the diagonal Gaussian momentum distribution
+        kin = torch.exp(-0.5 * ((p * p - p0 * p0) / mass).sum(dim=1))
+        prob = cpdf * kin / pdf
+        prob = torch.where(torch.isnan(prob), torch.zeros_like(prob), prob)      # hmc.py:58-59
+        state, pdf = _metropolis_accept(state, pdf, q, cpdf, prob, u[:, -1], accepted)
+        if chain is not None and t % thin == 0:
+            chain[:, t // thin] = state
+    last.copy_(state)
+    total += accepted.sum()
+    return chain, last, accepted, total

@@ -3,7 +3,9 @@
 `DefaultMetropolis(ndim, target, proposal=None)`: accept with min(1, pdf(cand)/pdf(state)).
 Device kernel: target = a built-in density (or its bound `pdf`), proposal =
 `proposals.Gaussian` with a diagonal covariance (random walk), `proposals.UniformLocal`, or
-the reference's default `densities.Uniform` independence proposal.
+the reference's default `densities.Uniform` independence proposal.  Any other target (a user
+`Density` subclass or a callable pdf taking (C, ndim) CUDA tensors) runs the generic path of
+`ensemble.run_rwm_generic`: one round of launches per step, vectorised over the ensemble.
 """
 import numpy as np
 
@@ -54,8 +56,15 @@ class DefaultMetropolis(MetropolisUpdate):
     def _run_ensemble(self, x0, sample_size, thin, store_chain, first_chain, replay):
         dens = as_builtin(self.target) or as_builtin(self.pdf)
         if dens is None:
-            raise TypeError("DefaultMetropolis on the device needs a built-in target density (Camel, "
-                            "UnconstrainedCamel, Banana, Gaussian, Uniform); there is no CPU fallback.")
+            # user-defined target: per-step launches, the user's pdf runs on the (C, ndim) CUDA tensor
+            if self.is_adaptive or replay is not None or not callable(self.pdf):
+                raise TypeError("a user-defined target needs a callable pdf; adaptive updates and replay tapes "
+                                "are available for the built-in densities only")
+            from ..integration.multi_channel import MultiChannel
+            if isinstance(self._proposal, MultiChannel):
+                raise TypeError("importance-sampling Metropolis over a MultiChannel proposal needs a built-in target")
+            kind, params = self._proposal_params()
+            return ensemble.run_rwm_generic(self.pdf, x0, kind, params, sample_size, thin, store_chain, first_chain)
         if dens.ndim != self.ndim:
             raise ValueError('target must have dimension ' + str(self.ndim))
         if self.is_adaptive:

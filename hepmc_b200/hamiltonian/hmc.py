@@ -63,14 +63,19 @@ class HamiltonianUpdate(MetropolisUpdate):
     def _run_ensemble(self, x0, sample_size, thin, store_chain, first_chain, replay):
         from ..surrogate.extreme_learning import SurrogateGradient
         tgt = self.target_density
-        if not isinstance(tgt, BuiltinDensity) or "pdf" in vars(tgt):
-            raise TypeError("HamiltonianUpdate on the device needs a built-in target density; "
-                            "there is no CPU fallback.")
+        user_target = not isinstance(tgt, BuiltinDensity) or "pdf" in vars(tgt)
         if not isinstance(self.p_dist, Gaussian):
             raise TypeError("the momentum distribution must be densities.Gaussian")
         if np.any(self.p_dist.mean != 0):
             raise TypeError("the momentum distribution must have zero mean")
         mass = self.p_dist._diag()
+        if user_target:
+            # user-defined target: per-step launches, the user's pdf / pot_gradient run on (C, ndim) CUDA tensors
+            if replay is not None or not (callable(getattr(tgt, "pdf", None)) and callable(getattr(tgt, "pot_gradient", None))):
+                raise TypeError("a user-defined HMC target needs callable pdf and pot_gradient taking (C, ndim) CUDA "
+                                "tensors; replay tapes are available for the built-in densities only")
+            return ensemble.run_hmc_generic(tgt.pdf, tgt.pot_gradient, x0, mass, float(self.step_size), int(self.steps),
+                                            sample_size, thin, store_chain, first_chain)
         grad = vars(tgt).get("pot_gradient", None)
         grad = getattr(grad, "fn", grad)            # unwrap util.count_calls
         elm_blk, keep = None, None

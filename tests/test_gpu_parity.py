@@ -513,8 +513,61 @@ def test_metropolis_options_and_default_proposal():
     met = H.DefaultMetropolis(1, H.densities.Uniform(1))
     s = met.sample(1000, 0.1)
     assert s.data.shape == (1000, 1) and abs(s.mean[0] - 0.5) < 0.06
-    with pytest.raises(TypeError):
-        H.DefaultMetropolis(1, lambda x: 1).sample(10, 0.1)  # no host loop / CPU fallback
+
+
+def test_user_defined_targets_run_the_generic_ensemble_path():
+    """Targets that are not built-in densities (user classes / callables on CUDA tensors): per-step
+    launches vectorised over the ensemble -- RWM and HMC, moments of known distributions, global
+    chain indices (a sub-ensemble reproduces the same chains), NumPy-only code via host_function."""
+    import torch
+
+    class Ring(H.Density):                      # unnormalised ring of radius 2, width 0.3
+        def __init__(self):
+            super().__init__(2)
+
+        def pdf(self, xs):
+            r = torch.sqrt((xs ** 2).sum(dim=1))
+            return torch.exp(-0.5 * ((r - 2.0) / 0.3) ** 2)
+
+    H.seed(31)
+    met = H.DefaultMetropolis(2, Ring(), H.proposals.Gaussian(2, cov=0.5 * np.eye(2)))
+    x0 = np.tile([2.0, 0.0], (4000, 1))
+    s = met.sample(300, x0, store_chain=False)
+    r = np.sqrt((s.data[:, 0] ** 2).sum(axis=1))
+    assert abs(r.mean() - 2.02) < 0.03 and abs(r.std() - 0.3) < 0.03       # E r = 2 + 0.09/2 for the 2-D ring
+    assert np.all(np.abs(s.data[:, 0].mean(axis=0)) < 0.2)
+    assert 0.1 < s.accepted.mean() / 300 < 0.9
+    H.seed(31)
+    sub = met.sample(300, x0[:7], store_chain=False)
+    assert np.array_equal(sub.data, s.data[:7]) and np.array_equal(sub.accepted, s.accepted[:7])
+    one = met.sample(50, [2.0, 0.0])                                         # the reference's single-chain call
+    assert one.data.shape == (50, 2) and isinstance(one.accepted, int)
+
+    class Normal3(H.Density):                   # standard normal with a hand-written gradient
+        def __init__(self):
+            super().__init__(3)
+
+        def pdf(self, xs):
+            return torch.exp(-0.5 * (xs ** 2).sum(dim=1))
+
+        def pot_gradient(self, xs):
+            return xs
+
+    H.seed(32)
+    hmc = H.hamiltonian.HamiltonianUpdate(Normal3(), H.densities.Gaussian(3), 10, 0.2)
+    s = hmc.sample(60, np.zeros((5000, 3)), store_chain=False)
+    pts = s.data[:, 0]
+    assert np.all(np.abs(pts.mean(axis=0)) < 0.06) and np.all(np.abs(pts.var(axis=0) - 1) < 0.08)
+    assert s.accepted.mean() / 60 > 0.8
+
+    def numpy_pdf(xs):
+        return np.exp(-0.5 * np.sum(np.asarray(xs) ** 2, axis=1))
+    H.seed(33)
+    s = H.DefaultMetropolis(2, H.util.host_function(numpy_pdf), H.proposals.Gaussian(2, cov=np.eye(2))).sample(
+        200, np.zeros((500, 2)), store_chain=False)
+    assert abs(s.data[:, 0].var(axis=0).mean() - 1) < 0.2
+    with pytest.raises(TypeError):                                           # replay tapes need a built-in target
+        met.sample(10, x0[:2], replay=(np.zeros((2, 9, 2)), np.zeros((2, 9))))
 
 
 def test_metropolis_ks_against_reference_sample():
