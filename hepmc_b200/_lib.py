@@ -81,6 +81,7 @@ SIGNATURES = {
     "hepmc_mc3_chains": (_int, [_dens_p, _vp, _int, _dbl, _int, ctypes.POINTER(_dbl), _dbl, _int, _elm_p, _int, _vp,
                                 _i64, _i64, _i64, _i64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hepmc_elm_eval": (_int, [_elm_p, _int, _int, _int, _vp, _i64, _vp, _vp]),
+    "hepmc_gather_rows": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
     "hepmc_autocov": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _i64, _i64, _vp, _vp]),
     "hepmc_effective_sample_size": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp]),
     "hepmc_histogramdd": (_int, [_vp, _i64, _int, _vp, ctypes.POINTER(_int), _vp, _vp]),

@@ -143,15 +143,19 @@ class MultiChannelMC(object):
         m2 = len(eval_count_2)
         ws_est = np.empty(eval_counts.size)
         estimates = np.empty(eval_counts.size)
+        kept = []
         for j, eval_count in enumerate(eval_counts):
             xs, values, weights, est, w = self.iterate(fn, eval_count, j < m2, True, keep_samples,
                                                        replay[it] if replay else None)
             it += 1
             estimates[j], ws_est[j] = est, w
             if keep_samples:
-                sample.extend_array('function_values', values)
-                sample.extend_array('weights', weights)
-                sample.extend_array('data', xs)
+                kept.append((values, weights, xs))
+        if kept:
+            # one concatenation at the end (extend_array per iteration copies everything again each time)
+            cat = (lambda parts: torch.cat(parts, dim=0)) if isinstance(kept[0][2], torch.Tensor) else \
+                (lambda parts: np.concatenate(parts, axis=0))
+            sample.function_values, sample.weights, sample.data = (cat([k[i] for k in kept]) for i in range(3))
         if eval_counts.size:
             if self.var_weighted:
                 variances = (ws_est - estimates ** 2) / eval_counts

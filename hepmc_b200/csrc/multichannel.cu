@@ -181,6 +181,19 @@ __global__ void __launch_bounds__(128) mc_accumulate_kernel(const __grid_constan
     }
 }
 
+// out[i, :] = src[order[i], :]: the by-channel grouping of a multi-channel sample
+// (multi_channel.py:141-150 returns the points channel by channel).  One thread per output
+// element pair; reads are gathered, writes coalesced.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const double* __restrict__ src, const int64_t* __restrict__ order,
+                                                          int64_t n, int row_len, double* __restrict__ out) {
+    const int64_t total = n * row_len;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / row_len;
+        const int k = (int)(e - i * row_len);
+        out[e] = src[order[i] * row_len + k];
+    }
+}
+
 }  // namespace hepmc
 
 using namespace hepmc;
@@ -244,6 +257,19 @@ int hepmc_multichannel_accumulate(const double* f_dev, const double* p_dev, cons
     const size_t smem = 2 * (size_t)n_channels * 128 * 8;
     HEPMC_CUDA(cudaFuncSetAttribute(mc_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     mc_accumulate_kernel<<<blocks, 128, smem, as_stream(stream)>>>(a);
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+int hepmc_gather_rows(const double* src_dev, const int64_t* order_dev, int64_t n, int row_len, double* out_dev,
+                      void* stream) {
+    HEPMC_REQUIRE(n >= 0 && row_len >= 1, HEPMC_E_ARG, "hepmc_gather_rows: bad sizes");
+    if (n == 0) return 0;
+    HEPMC_REQUIRE(src_dev && order_dev && out_dev, HEPMC_E_ARG, "hepmc_gather_rows: NULL buffer");
+    int64_t blocks = (n * row_len + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    gather_rows_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src_dev, order_dev, n, row_len, out_dev);
     HEPMC_LAUNCH_CHECK();
     return 0;
 }

@@ -223,6 +223,12 @@ int hepmc_rambo_diet_inverse(int nparticles, double e_cm, int64_t n, const doubl
 int hepmc_accept_flags(const double* f_dev, const double* q_dev, double q_scalar, double bound, int64_t n,
                        int64_t first_index, uint64_t seed, uint32_t stream_id, unsigned char* flags_dev, void* stream);
 
+/* out_dev[i, :] = src_dev[order_dev[i], :] for rows of row_len doubles: the by-channel grouping of a
+ * multi-channel sample (MultiChannel.rvs / ChannelsSample return the points channel by channel,
+ * multi_channel.py:141-150); order_dev = positions of channel 0's points, then channel 1's, ... */
+int hepmc_gather_rows(const double* src_dev, const int64_t* order_dev, int64_t n, int row_len,
+                      double* out_dev, void* stream);
+
 /* ---- random-walk Metropolis ensembles: replaces MarkovUpdate.sample (base.py:44-97)
  * + MetropolisUpdate.next_state/accept (metropolis.py:37-50,76-95) + DefaultMetropolis.
  * proposal (:122-124) + proposals.Gaussian.proposal (gaussian.py:25-27), one chain per
