@@ -261,14 +261,17 @@ static int pick_threads(int ndim, int K, size_t& smem) {
     return 0;
 }
 
-static int check_sample_common(const char* who, int ndim, int K, int64_t n, int64_t first_index, int64_t chunk) {
+// aligned = false: pure draw generation (no integrand, no partial rows), where the chunk grid carries no
+// reduction order and first_index may be any global index (per-chain draws of the generic chain path)
+static int check_sample_common(const char* who, int ndim, int K, int64_t n, int64_t first_index, int64_t chunk,
+                               bool aligned = true) {
     HEPMC_REQUIRE(ndim >= 1 && ndim <= HEPMC_MAX_DIM, HEPMC_E_UNSUPPORTED, "%s: ndim %d outside [1,%d]", who, ndim,
                   HEPMC_MAX_DIM);
     HEPMC_REQUIRE(K >= 1 && K <= HEPMC_MAX_DIVISIONS, HEPMC_E_UNSUPPORTED, "%s: divisions %d outside [1,%d]", who, K,
                   HEPMC_MAX_DIVISIONS);
     HEPMC_REQUIRE(n >= 0 && first_index >= 0, HEPMC_E_ARG, "%s: negative n/first_index", who);
     HEPMC_REQUIRE(chunk >= 256 && chunk % 256 == 0, HEPMC_E_ARG, "%s: chunk must be a positive multiple of 256", who);
-    HEPMC_REQUIRE(first_index % chunk == 0, HEPMC_E_ARG, "%s: first_index must be a multiple of chunk", who);
+    HEPMC_REQUIRE(!aligned || first_index % chunk == 0, HEPMC_E_ARG, "%s: first_index must be a multiple of chunk", who);
     return 0;
 }
 
@@ -332,7 +335,8 @@ int hepmc_plain_mc_sample(const hepmc_density_t* dens, int64_t n, int64_t first_
                           uint64_t seed, uint32_t stream_id, const double* u_replay_dev,
                           double* data_dev, double* f_dev, double* partials_dev, void* stream) {
     HEPMC_REQUIRE(dens != nullptr, HEPMC_E_ARG, "hepmc_plain_mc_sample: dens is NULL");
-    int e = check_sample_common("hepmc_plain_mc_sample", dens->ndim, 1, n, first_index, chunk);
+    int e = check_sample_common("hepmc_plain_mc_sample", dens->ndim, 1, n, first_index, chunk,
+                                dens->kind != HEPMC_NONE);
     if (e) return e;
     HEPMC_REQUIRE(dens->kind >= HEPMC_CAMEL && dens->kind <= HEPMC_NONE, HEPMC_E_ARG, "bad density kind %d", dens->kind);
     HEPMC_REQUIRE(dens->kind == HEPMC_NONE || partials_dev, HEPMC_E_ARG, "hepmc_plain_mc_sample: partials_dev is NULL");

@@ -109,7 +109,9 @@ int64_t hepmc_default_chunk(int64_t n_total);
  * Optional outputs data_dev (n, ndim), f_dev (n,).  Per-chunk deterministic partials
  * (count, mean, M2) are written to partials_dev[(n_chunks) x 3], n_chunks =
  * ceil(n / chunk); chunk boundaries are relative to first_index, which must be a
- * multiple of chunk.  dens->kind == HEPMC_NONE: draw data only (two-kernel path). */
+ * multiple of chunk.  dens->kind == HEPMC_NONE: draw data only (two-kernel path); no partial rows
+ * are written, so first_index may then be any global index (point i always uses counter
+ * first_index + i). */
 int hepmc_plain_mc_sample(const hepmc_density_t* dens, int64_t n, int64_t first_index, int64_t chunk,
                           uint64_t seed, uint32_t stream_id, const double* u_replay_dev,
                           double* data_dev, double* f_dev, double* partials_dev, void* stream);

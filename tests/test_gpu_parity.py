@@ -1082,3 +1082,29 @@ def test_sample_repr_for_an_ensemble():
     # one chain of the ensemble analysed alone gives the same effective sample size
     from hepmc_b200.core.util import stat_tools
     assert np.array_equal(stat_tools.effective_sample_size(s.data[5], tgt.mean, tgt.variance), ess[5])
+
+
+def test_generic_path_output_options():
+    """thin= / store_chain= / first_chain= on the user-target path behave like on the kernels."""
+    import torch
+
+    def pdf(xs):
+        return torch.exp(-0.5 * ((xs - 1.0) ** 2).sum(dim=1))
+    met = H.DefaultMetropolis(2, pdf, H.proposals.UniformLocal(2, 0.5, sample_range=(-5, 7)))
+    x0 = np.zeros((50, 2))
+    H.seed(3)
+    full = met.sample(41, x0)
+    H.seed(3)
+    thin = met.sample(41, x0, thin=8)
+    H.seed(3)
+    last = met.sample(41, x0, store_chain=False)
+    assert full.data.shape == (50, 41, 2) and thin.data.shape == (50, 6, 2)
+    assert np.array_equal(thin.data, full.data[:, ::8]) and np.array_equal(last.data[:, 0], full.data[:, -1])
+    assert np.array_equal(full.accepted, last.accepted) and int(full.total_accepted.item()) == int(full.accepted.sum())
+    H.seed(3)
+    shard = met.sample(41, x0[10:20], first_chain=10)
+    assert np.array_equal(shard.data, full.data[10:20])
+    # every coordinate moves by the same uniform: increments along the diagonal, inside the box
+    steps = np.diff(full.data, axis=1)
+    moved = np.abs(steps).sum(axis=2) > 0
+    assert np.allclose(steps[moved][:, 0], steps[moved][:, 1]) and full.data.min() >= -5 and full.data.max() <= 7
