@@ -221,3 +221,89 @@ def run_hmc_generic(pdf_fn, grad_fn, x0, mass_diag, step_size, steps, sample_siz
     last.copy_(state)
     total += accepted.sum()
     return chain, last, accepted, total
+
+
+def run_mixing_generic(pdf_fn, channels, beta, local, x0, sample_size, thin=1, store_chain=True, first_chain=0):
+    """MixingMarkovUpdate([IS-Metropolis over `channels`, local update]) for a user-defined target
+    (base.py:169-179 + metropolis.py:37-50): per step every chain picks the importance-sampling update
+    with probability beta, else the local one (DefaultMetropolis with a Gaussian / UniformLocal
+    proposal, or HamiltonianUpdate with the user's pot_gradient).  Both candidates are produced for the
+    whole ensemble (kernels), the user's pdf is called ONCE per step on the selected candidates."""
+    from ..proposals import Gaussian as GaussianProposal, UniformLocal
+    from .metropolis import DefaultMetropolis
+    from ..integration.engine import none_block
+    dev = x0.device
+    C, ndim = x0.shape
+    chain, last, accepted, total = alloc_outputs(C, ndim, sample_size, thin, store_chain, dev)
+    is_hmc = not isinstance(local, DefaultMetropolis) and local is not None
+    if local is None:
+        if beta < 1.0:
+            raise TypeError("a local update is needed when beta < 1")
+    elif is_hmc:
+        tgt = local.target_density
+        if not callable(getattr(tgt, "pot_gradient", None)):
+            raise TypeError("the local HamiltonianUpdate needs a target with a callable pot_gradient")
+        mass = torch.as_tensor(np.array(local.p_dist._diag(), dtype=np.float64), device=dev)
+        step_size, steps = float(local.step_size), int(local.steps)
+    elif isinstance(local._proposal, GaussianProposal):
+        cov = np.asarray(local._proposal.cov)
+        if np.count_nonzero(cov - np.diag(np.diagonal(cov))):
+            raise TypeError("the local random walk needs a diagonal proposal covariance")
+        scale = torch.as_tensor(np.sqrt(np.diagonal(cov)), device=dev)
+    elif isinstance(local._proposal, UniformLocal):
+        par = torch.as_tensor(np.array(local._proposal._kernel_params(), dtype=np.float64), device=dev)
+    else:
+        raise TypeError("the local update must be HamiltonianUpdate or DefaultMetropolis with proposals.Gaussian / "
+                        "proposals.UniformLocal, got " + type(local).__name__)
+    npair = (ndim + 1) // 2
+    sid0 = rng.next_stream(2 * max(sample_size - 1, 1))        # per step: one stream for the mixture draw, one for the rest
+    table = channels._table()
+    blk = none_block(ndim)
+    chunk = _lib.default_chunk(C)
+    state = x0.clone()
+    pdf = _user_values(pdf_fn, state, "pdf").reshape(C)
+    if chain is not None:
+        chain[:, 0] = state
+    is_cand = torch.empty((C, ndim), dtype=torch.float64, device=dev)
+    q_cand = torch.empty(C, dtype=torch.float64, device=dev)
+    ch = torch.empty(C, dtype=torch.int64, device=dev)
+    for t in range(1, sample_size):
+        u = _step_draws(C, 2 * npair + 2, first_chain, sid0 + 2 * (t - 1), dev)
+        pick_is = u[:, -2] < beta                                            # base.py:170
+        # importance-sampling candidate ~ mixture, with q(candidate) from the same kernel
+        _lib.call("hepmc_multichannel_sample", ctypes.byref(blk), _lib.ptr(table), channels.count, ndim,
+                  C, int(first_chain), chunk, rng.get_seed(), sid0 + 2 * (t - 1) + 1, None, None,
+                  _lib.ptr(is_cand), None, _lib.ptr(q_cand), _lib.ptr(ch), None, None, _lib.stream_ptr())
+        if local is None:
+            loc_cand, kin = is_cand, None
+        elif is_hmc:
+            p0 = torch.sqrt(mass) * _normals(u, ndim)
+            q, p = state.clone(), p0.clone()
+            g = _user_values(tgt.pot_gradient, q, "pot_gradient").reshape(C, ndim)
+            for _ in range(steps):
+                p = p - (step_size / 2) * g
+                q = q + step_size * (p / mass)
+                g = _user_values(tgt.pot_gradient, q, "pot_gradient").reshape(C, ndim)
+                p = p - (step_size / 2) * g
+            loc_cand = q
+            kin = torch.exp(-0.5 * ((p * p - p0 * p0) / mass).sum(dim=1))
+        elif isinstance(local._proposal, GaussianProposal):
+            loc_cand, kin = state + scale * _normals(u, ndim), None
+        else:
+            delta, lo, hi = par[:ndim], par[ndim], par[ndim + 1]
+            loc_cand = torch.minimum(torch.clamp(state - delta / 2, min=float(lo)), hi - delta) + u[:, :1] * delta
+            kin = None
+        cand = torch.where(pick_is[:, None], is_cand, loc_cand)
+        cpdf = _user_values(pdf_fn, cand, "pdf").reshape(C)
+        q_state = channels.pdf(state).reshape(C)
+        prob_is = cpdf * q_state / pdf / q_cand                              # metropolis.py:46-47
+        prob_loc = cpdf / pdf if kin is None else cpdf * kin / pdf
+        prob = torch.where(pick_is, prob_is, prob_loc)
+        if kin is not None:
+            prob = torch.where(torch.isnan(prob) & ~pick_is, torch.zeros_like(prob), prob)   # hmc.py:58-59
+        state, pdf = _metropolis_accept(state, pdf, cand, cpdf, prob, u[:, -1], accepted)
+        if chain is not None and t % thin == 0:
+            chain[:, t // thin] = state
+    last.copy_(state)
+    total += accepted.sum()
+    return chain, last, accepted, total

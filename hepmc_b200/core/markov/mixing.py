@@ -109,6 +109,11 @@ class MixingMarkovUpdate(MarkovUpdate):
             raise TypeError("updates[0] must be DefaultMetropolis(ndim, target[, MultiChannel(...)])")
         dens = as_builtin(is_upd.target) or as_builtin(is_upd.pdf)
         if dens is None:
-            raise TypeError("the mixed updates need a built-in target density; there is no CPU fallback")
+            # user-defined target: per-step launches, the user's pdf runs on the (C, ndim) CUDA tensor
+            if replay is not None or not callable(is_upd.pdf):
+                raise TypeError("a user-defined target needs a callable pdf; replay tapes are available for the "
+                                "built-in densities only")
+            return ensemble.run_mixing_generic(is_upd.pdf, channels, float(self.weights[0]), local, x0, sample_size,
+                                               thin, store_chain, first_chain)
         return run_mc3(dens, channels, float(self.weights[0]), local, x0, sample_size, thin, store_chain,
                        first_chain, replay)

@@ -209,10 +209,13 @@ int hepmc_multichannel_sample(const hepmc_density_t* dens, const double* channel
     HEPMC_REQUIRE(n_channels >= 1 && n_channels <= kMaxCh, HEPMC_E_UNSUPPORTED,
                   "hepmc_multichannel_sample: %d channels outside [1,%d]", n_channels, kMaxCh);
     HEPMC_REQUIRE(ndim >= 1 && ndim <= kChDim, HEPMC_E_UNSUPPORTED, "hepmc_multichannel_sample: ndim %d outside [1,%d]", ndim, kChDim);
-    HEPMC_REQUIRE(n >= 0 && first_index >= 0 && chunk >= 128 && chunk % 128 == 0 && first_index % chunk == 0, HEPMC_E_ARG,
+    HEPMC_REQUIRE(n >= 0 && first_index >= 0 && chunk >= 128 && chunk % 128 == 0, HEPMC_E_ARG,
                   "hepmc_multichannel_sample: bad n/first_index/chunk");
     HEPMC_REQUIRE((xs_replay_dev == nullptr) == (ch_replay_dev == nullptr), HEPMC_E_ARG, "replay needs xs and channel ids");
     const bool fused = dens->kind != HEPMC_NONE;
+    // partial rows follow the chunk grid; sample-only calls write none and may start anywhere
+    HEPMC_REQUIRE(!(fused || stats_partials_dev || ch_partials_dev) || first_index % chunk == 0, HEPMC_E_ARG,
+                  "hepmc_multichannel_sample: first_index must be a multiple of chunk when partials are written");
     HEPMC_REQUIRE(!fused || dens->ndim == ndim, HEPMC_E_ARG, "integrand ndim %d != channel ndim %d", dens->ndim, ndim);
     HEPMC_REQUIRE(!fused || (stats_partials_dev && ch_partials_dev), HEPMC_E_ARG, "partial buffers are NULL");
     HEPMC_REQUIRE(fused || (x_dev && p_dev && ch_dev), HEPMC_E_ARG, "two-kernel path needs x, p and channel outputs");
