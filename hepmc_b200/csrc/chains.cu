@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(128) rwm_kernel(const __grid_constant__ Dens d
         if (a.chain) store_state<NDIM>(a.chain, c, a.n_kept, 0, x);
         for (int64_t t = 1; t < a.T; ++t) {
             double cand[NDIM];
+            double u_spare = 0.5;
             double z[NDIM];  // standard normals (random walk) or uniforms (independence proposal)
             if (a.z_replay) {
                 const double* zt = a.z_replay + ((size_t)c * (a.T - 1) + (t - 1)) * NDIM;
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(128) rwm_kernel(const __grid_constant__ Dens d
                 for (int k = 0; k < NCALL; ++k) {
                     const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(t - 1) * CPS + k,
                                                a.stream_id, key);
+                    if (k == 0) u_spare = u24_spare(r.x, r.z);
                     double z0, z1;
                     if (a.prop_kind == 0) {
                         normal_pair(r, z0, z1);
@@ -67,14 +69,8 @@ __global__ void __launch_bounds__(128) rwm_kernel(const __grid_constant__ Dens d
             }
             const double cpdf = density_pdf_n<NDIM>(dens, cand);
             const double ratio = cpdf / pdf;  // metropolis.py:50
-            double u;
-            if (a.u_replay) {
-                u = a.u_replay[(size_t)c * (a.T - 1) + (t - 1)];
-            } else {
-                const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(t - 1) * CPS + NCALL,
-                                           a.stream_id, key);
-                u = u52(r.x, r.y);
-            }
+            // native mode: the accept uniform comes from the spare bits of the proposal draw (common.cuh)
+            const double u = a.u_replay ? a.u_replay[(size_t)c * (a.T - 1) + (t - 1)] : u_spare;
             if (ratio >= 1.0 || u < ratio) {  // metropolis.py:87 (NaN -> reject)
                 bool changed = false;
 #pragma unroll

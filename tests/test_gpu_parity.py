@@ -463,7 +463,7 @@ def test_uniform_local_metropolis():
     s = met.sample(T, x0, first_chain=7)
     w = O.philox_words(77, 0, 7 + np.arange(C), 2 * (T - 1)).astype(np.uint32)
     vv = O.u52(w[:, 0::2, 0], w[:, 0::2, 1])
-    uu = O.u52(w[:, 1::2, 0], w[:, 1::2, 1])
+    uu = O.u24_spare(w[:, 0::2, 0], w[:, 0::2, 2])
     chain, acc = O.uniform_local_chains(O.camel_pdf, x0, vv, uu, delta)
     assert np.array_equal(s.accepted, acc)
     assert_close(s.data, chain, 1e-12, atol=1e-15)
@@ -481,7 +481,7 @@ def test_metropolis_native_matches_oracle_draws():
     x0 = np.tile([0., 10.], (C, 1))
     met = H.DefaultMetropolis(2, H.densities.Banana(2), H.proposals.Gaussian(2, cov=10 * np.eye(2)))
     s = met.sample(T, x0, first_chain=100)
-    # oracle draws: per step 2 Philox calls (normals, accept uniform)
+    # oracle draws: per step one Philox call (counter stride 2): normals, accept uniform from its spare bits
     idx = 100 + np.arange(C)
     w = O.philox_words(31337, 0, idx, 2 * (T - 1)).astype(np.uint32)
     z = np.empty((C, T - 1, 2))
@@ -489,7 +489,7 @@ def test_metropolis_native_matches_oracle_draws():
     for t in range(T - 1):
         z0, z1 = O.box_muller(O.u52(w[:, 2 * t, 0], w[:, 2 * t, 1]), O.u52(w[:, 2 * t, 2], w[:, 2 * t, 3]))
         z[:, t, 0], z[:, t, 1] = z0, z1
-        u[:, t] = O.u52(w[:, 2 * t + 1, 0], w[:, 2 * t + 1, 1])
+        u[:, t] = O.u24_spare(w[:, 2 * t, 0], w[:, 2 * t, 2])
     chain, acc = O.metropolis_chains(O.banana_pdf, x0, z, u, np.sqrt([10., 10.]))
     assert np.array_equal(s.accepted, acc)
     assert_close(s.data, chain, 1e-10, atol=1e-10)
@@ -927,7 +927,7 @@ def test_edge_cases_maximum_sizes():
         for k in range(8):
             z0, z1 = O.box_muller(O.u52(w[:, 9 * t + k, 0], w[:, 9 * t + k, 1]), O.u52(w[:, 9 * t + k, 2], w[:, 9 * t + k, 3]))
             z[:, t, 2 * k], z[:, t, 2 * k + 1] = z0, z1
-        u[:, t] = O.u52(w[:, 9 * t + 8, 0], w[:, 9 * t + 8, 1])
+        u[:, t] = O.u24_spare(w[:, 9 * t, 0], w[:, 9 * t, 2])      # spare bits of the step's first proposal call
     chain, acc = O.metropolis_chains(lambda x: O.gaussian_pdf(x, 0.5, 0.01), x0, z, u, np.full(nd, 0.02))
     assert np.array_equal(s.accepted, acc)
     assert_close(s.data, chain, 1e-10, atol=1e-12)

@@ -276,3 +276,10 @@ def test_bin_wise_chi2_restatement():
             assert n == int(ref[2])
             assert_close(red, ref[0], 1e-12)
             assert_close(p, ref[1], 1e-9)
+
+
+def test_spare_bit_uniform():
+    a = np.array([0, 0xffffffff, 0x12345abc], dtype=np.uint32)
+    c = np.array([0, 0xffffffff, 0x9abcd123], dtype=np.uint32)
+    u = O.u24_spare(a, c)
+    assert u[0] == 2.0 ** -25 and u[1] == 1.0 - 2.0 ** -25 and u[2] == (0xabc * 4096 + 0x123 + 0.5) * 2.0 ** -24
