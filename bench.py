@@ -251,9 +251,9 @@ def run_b200(args):
         "roofline": {"bound": "fp64_simt", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size from the ncu
-                     # --set full capture (profiles/r01_vegas_sample_kernel_ncu_summary.txt): 94 KB + 8.01 MB;
+                     # --set full capture (profiles/r01_vegas_sample_kernel_ncu_summary.txt): 70.7 KB + 9.28 MB;
                      # the 59 MB of partial rows mostly stay in L2 until the reduce kernels read them
-                     "traffic": 8108288 if (n_local == N_POINTS and world == 1) else None,
+                     "traffic": 9354752 if (n_local == N_POINTS and world == 1) else None,
                      "kernel": "vegas_sample_kernel", "kernel_ms": kernel_ms, "points_per_launch": n_local,
                      "flop_per_point": FLOP_PER_POINT,
                      "peak_source": "live DFMA probe (hepmc_fp64_probe); MEASURED_PEAKS.json has no FP64 entry "
