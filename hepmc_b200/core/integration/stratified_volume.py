@@ -1,5 +1,6 @@
 """Separable grid on the unit hypercube: the VEGAS sampling distribution
-(hepmc/core/integration/stratified_volume.py:11-182, the parts VEGAS / ImportanceMC use).
+(hepmc/core/integration/stratified_volume.py:11-182), and the partition of StratifiedMC
+(per-bin base counts, `iterate`).
 
 State = per axis the bin boundaries `bounds[d]` (K+1) and widths `sizes[d]` (K).  A bin is
 chosen uniformly per axis and the point uniformly inside it; pdf = 1 / (K^ndim * volume).
@@ -21,9 +22,8 @@ from . import engine
 class GridVolumes(Distribution):
 
     def __init__(self, bounds=None, base_counts=None, default_base_count=1, ndim=1, divisions=1):
-        if base_counts:
-            raise NotImplementedError("per-bin base counts belong to StratifiedMC (out of scope)")
-        self.base_counts = dict()
+        # {multi-index tuple: base number of samples}; bins not listed use default_base_count (:13-37)
+        self.base_counts = dict(base_counts) if base_counts else dict()
         self.default_base_count = default_base_count
         self._grid = None       # device tensor (ndim, 2K+1), created on first device use
         self._host = None       # float64 array (ndim, 2K+1): the authoritative copy until then
@@ -56,7 +56,9 @@ class GridVolumes(Distribution):
         self._grid = None
         k = (self._host.shape[1] - 1) // 2
         self.partition_count = float(k) ** self.ndim   # floating point: no int64 overflow (App. B1)
-        self.total_base_count = self.default_base_count * self.partition_count
+        # _update_total_base_count, :149-155
+        self.total_base_count = (sum(self.base_counts.values()) +
+                                 self.default_base_count * (self.partition_count - len(self.base_counts)))
 
     def device_grid(self):
         """The (ndim, 2K+1) CUDA tensor the kernels use (authoritative once created)."""
@@ -130,15 +132,68 @@ class GridVolumes(Distribution):
         x, _, _ = self._sample(int(sample_count), False)
         return config.deliver(x.t().contiguous())
 
+    # ---- stratified partition (StratifiedMC) ---------------------------------------
+    def get_count(self, index, multiple=1):
+        """Samples of bin `index` (:127-134; a non-integer multiple truncates)."""
+        return int(multiple * self.base_counts.get(tuple(int(i) for i in index), self.default_base_count))
+
+    def _cells(self, multiple=1):
+        """All bins in np.ndindex order: counts (n_cells,), lower / upper corners (n_cells, ndim)."""
+        k = self.divisions
+        b = np.stack(self.bounds)
+        index = np.stack(np.unravel_index(np.arange(k ** self.ndim), (k,) * self.ndim), axis=1)
+        counts = np.full(index.shape[0], int(multiple * self.default_base_count), dtype=np.int64)
+        for key, value in self.base_counts.items():
+            counts[np.ravel_multi_index(tuple(int(i) for i in key), (k,) * self.ndim)] = int(multiple * value)
+        lower = np.stack([b[d][index[:, d]] for d in range(self.ndim)], axis=1)
+        upper = np.stack([b[d][index[:, d] + 1] for d in range(self.ndim)], axis=1)
+        return counts, lower, upper
+
+    def _cell_points(self, counts, lower, upper, replay=None):
+        """One batch for all bins: uniforms from the native generator (or the replay tape), mapped
+        into each bin; returns the (N, ndim) CUDA tensor and the bin id of every point."""
+        dev = _lib.device()
+        n = int(counts.sum())
+        if replay is not None:
+            u, _ = _lib.to_device(np.concatenate([np.asarray(r, dtype=np.float64).reshape(-1, self.ndim) for r in replay]))
+            if u.shape[0] != n:
+                raise ValueError("replay holds %d points, the partition needs %d" % (u.shape[0], n))
+        else:
+            u = engine.uniform_rvs(n, self.ndim)
+        cell = torch.repeat_interleave(torch.arange(counts.shape[0], device=dev), torch.as_tensor(counts, device=dev))
+        lo = torch.as_tensor(lower, device=dev)[cell]
+        hi = torch.as_tensor(upper, device=dev)[cell]
+        return lo + (hi - lo) * u, cell                      # :143 lower + (upper - lower) * rand
+
+    def iterate(self, multiple=1, replay=None):
+        """Yield (count, samples (count, ndim), volume) bin by bin (:136-147)."""
+        counts, lower, upper = self._cells(multiple)
+        xs, _ = self._cell_points(counts, lower, upper, replay)
+        start = 0
+        for c, lo, hi in zip(counts, lower, upper):
+            yield int(c), config.deliver(xs[start:start + int(c)]), float(np.prod(hi - lo))
+            start += int(c)
+
     # ---- density ----------------------------------------------------------------
+    def _count_factor(self, idx):
+        """count(bin) / default_base_count for (ndim, N) bin indices on any device."""
+        fac = torch.ones(idx.shape[1], dtype=torch.float64, device=idx.device)
+        for key, value in self.base_counts.items():
+            hit = torch.ones(idx.shape[1], dtype=torch.bool, device=idx.device)
+            for d in range(self.ndim):
+                hit &= idx[d] == int(key[d])
+            fac = torch.where(hit, torch.full_like(fac, value / self.default_base_count), fac)
+        return fac
+
     def pdf_indices(self, indices):
-        idx = torch.as_tensor(np.asarray(indices) if not isinstance(indices, torch.Tensor) else indices)
+        """count / total_base_count / volume of the given bins (:67-72)."""
+        idx = torch.as_tensor(np.asarray(indices) if not isinstance(indices, torch.Tensor) else indices).cpu().long()
         st = torch.as_tensor(self._state_host())
         k = self.divisions
         vols = torch.ones(idx.shape[1], dtype=torch.float64)
         for d in range(self.ndim):
-            vols = vols * st[d, k + 1:][idx[d].cpu().long()]
-        out = self.default_base_count / self.total_base_count / vols
+            vols = vols * st[d, k + 1:][idx[d]]
+        out = self.default_base_count * self._count_factor(idx) / self.total_base_count / vols
         return out.numpy()
 
     def pdf(self, xs):
@@ -149,6 +204,13 @@ class GridVolumes(Distribution):
         if x_dev.shape[0]:
             _lib.call("hepmc_grid_pdf", _lib.ptr(self.device_grid()), self.ndim, self.divisions, _lib.ptr(x_dev),
                       x_dev.shape[0], _lib.ptr(out), _lib.stream_ptr())
+            if self.base_counts:
+                # the kernel answers 1 / (K^ndim vol); bins with their own base count are rescaled
+                grid = self.device_grid()
+                k = self.divisions
+                idx = torch.stack([torch.bucketize(x_dev[:, d].contiguous(), grid[d, :k + 1].contiguous(), right=True) - 1
+                                   for d in range(self.ndim)]).clamp_(0, k - 1)
+                out = out * (self.default_base_count * self.partition_count / self.total_base_count) * self._count_factor(idx)
         return _lib.to_host_like(out, host)
 
     def pdf_gradient(self, xs):

@@ -714,6 +714,34 @@ def gen_stats(h):
     save("stats", **out)
 
 
+def gen_stratified(h):
+    """StratifiedMC over GridVolumes with uniform and per-bin base counts (stratified.py:68-91,
+    stratified_volume.py:127-155); the per-bin np.random.rand draws are taped."""
+    out = {}
+    cases = (
+        ("lin1", 1, 4, 10, {}, 5, lambda x: x),                              # tests/test_integration.py:68-76
+        ("camel2", 2, 5, 20, {(1, 1): 100, (3, 3): 60, (0, 4): 8}, 3, None),
+    )
+    for name, ndim, div, base, counts, multiple, fn in cases:
+        np.random.seed(SEED)
+        vol = h.GridVolumes(ndim=ndim, divisions=div, default_base_count=base, base_counts=dict(counts))
+        target = h.densities.Camel(ndim) if fn is None else None
+        with Tape() as t:
+            s = h.StratifiedMC(volumes=vol)(target if fn is None else fn, multiple)
+        out[name + "_u"] = np.concatenate([np.asarray(r).reshape(-1, ndim) for r in t.log["rand"]])
+        out[name + "_sizes"] = np.array(s.sub_sizes, dtype=np.int64)
+        out[name + "_integral"] = s.integral
+        out[name + "_err"] = s.integral_err
+        out[name + "_data"] = s.data
+        out[name + "_values"] = s.function_values
+        out[name + "_sub_weights"] = np.array(s.sub_weights)
+        xs = np.random.default_rng(3).random((64, ndim))
+        out[name + "_pdf_xs"] = xs
+        out[name + "_pdf"] = vol.pdf(xs)
+        out[name + "_total_base_count"] = vol.total_base_count
+    save("stratified", **out)
+
+
 def gen_importance_ideal(h):
     """tests/test_integration.py:44-52 -- the reference's only exact KAT."""
     np.random.seed(SEED)
@@ -739,6 +767,7 @@ def main():
     gen_mixing(h)
     gen_rambo_diet(h)
     gen_stats(h)
+    gen_stratified(h)
     gen_ks_reference()
 
 

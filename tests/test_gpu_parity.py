@@ -1159,3 +1159,42 @@ def test_mixing_with_a_user_defined_target():
     mc3 = H.mc3.BasicMC3(target, channels, H.DefaultMetropolis(2, target, H.proposals.Gaussian(2, cov=0.002 * np.eye(2))))
     res = mc3(([], [4000] * 3, []), 200, initial=[0.35, 0.3])
     assert res.data.shape == (200, 2) and abs(mc3.integration_sample.integral - 1.0) < 0.1
+
+
+# ------------------------------------------------------------------ StratifiedMC
+@pytest.mark.parametrize("name,ndim,div,base,counts,multiple", [
+    ("lin1", 1, 4, 10, {}, 5), ("camel2", 2, 5, 20, {(1, 1): 100, (3, 3): 60, (0, 4): 8}, 3)])
+def test_stratified_replay(name, ndim, div, base, counts, multiple):
+    g = G("stratified")
+    vol = H.GridVolumes(ndim=ndim, divisions=div, default_base_count=base, base_counts=counts)
+    assert vol.total_base_count == float(g[name + "_total_base_count"])
+    fn = (lambda x: x) if name == "lin1" else H.densities.Camel(ndim)
+    sizes = g[name + "_sizes"]
+    tape = np.split(g[name + "_u"], np.cumsum(sizes)[:-1])
+    s = H.StratifiedMC(volumes=vol)(fn, multiple, replay=tape)
+    assert s.sub_sizes == list(sizes)
+    assert_close(s.integral, g[name + "_integral"], 1e-12)
+    assert_close(s.integral_err, g[name + "_err"], 1e-11)
+    assert_close(s.data, g[name + "_data"], 1e-15)
+    assert_close(s.function_values, g[name + "_values"], RTOL)
+    assert_close(np.asarray(s.sub_weights), g[name + "_sub_weights"], 1e-13)
+    assert s.weights.shape == s.function_values.shape
+    assert_close(vol.pdf(g[name + "_pdf_xs"]), g[name + "_pdf"], 1e-13)
+    bins = np.stack([np.minimum((g[name + "_pdf_xs"][:, d] * div).astype(int), div - 1) for d in range(ndim)])
+    assert_close(vol.pdf_indices(bins), g[name + "_pdf"], 1e-13)
+    cells = list(vol.iterate(multiple, replay=tape))
+    assert [c[0] for c in cells] == list(sizes) and np.allclose(np.concatenate([c[1] for c in cells]), g[name + "_data"])
+
+
+def test_stratified_native():
+    """The reference's own tests (tests/test_integration.py:66-84) plus a 2-D integral with a known value."""
+    H.seed(19)
+    vol = H.GridVolumes(ndim=1, divisions=4, default_base_count=10)
+    s = H.StratifiedMC(volumes=vol)(lambda x: x, 5)
+    assert abs(s.integral - 0.5) < 0.05 and s.integral_err < 0.1 and s.data.shape == (200, 1)
+    vol = H.GridVolumes(ndim=1, divisions=4, default_base_count=100)
+    s = H.StratifiedMC(volumes=vol).get_interface_infer_multiple()(lambda x: x, 4000)
+    assert abs(s.integral - 0.5) < 0.02 and s.integral_err < 0.1 and s.data.shape == (4000, 1)
+    vol = H.GridVolumes(ndim=2, divisions=20, default_base_count=500)
+    s = H.StratifiedMC(volumes=vol)(H.densities.Camel(2), 2, keep_samples=False)
+    assert s.data is None and abs(s.integral - 1.0) < 5 * s.integral_err and s.integral_err < 5e-3

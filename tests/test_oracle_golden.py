@@ -283,3 +283,20 @@ def test_spare_bit_uniform():
     c = np.array([0, 0xffffffff, 0x9abcd123], dtype=np.uint32)
     u = O.u24_spare(a, c)
     assert u[0] == 2.0 ** -25 and u[1] == 1.0 - 2.0 ** -25 and u[2] == (0xabc * 4096 + 0x123 + 0.5) * 2.0 ** -24
+
+
+@pytest.mark.parametrize("name,ndim,div,base,counts,multiple", [
+    ("lin1", 1, 4, 10, {}, 5), ("camel2", 2, 5, 20, {(1, 1): 100, (3, 3): 60, (0, 4): 8}, 3)])
+def test_stratified_restatement(name, ndim, div, base, counts, multiple):
+    """stratified.py:68-91 + stratified_volume.py:67-83,127-155 with the reference's draws replayed."""
+    g = G("stratified")
+    bounds = [np.linspace(0, 1, div + 1) for _ in range(ndim)]
+    fn = (lambda xs: xs[:, 0]) if name == "lin1" else O.camel_pdf
+    sizes = g[name + "_sizes"]
+    tape = np.split(g[name + "_u"], np.cumsum(sizes)[:-1])
+    r = O.stratified_mc(fn, bounds, tape, multiple, base, counts)
+    assert np.array_equal(r["sizes"], sizes)
+    assert_close(r["integral"], g[name + "_integral"], 1e-13)
+    assert_close(r["integral_err"], g[name + "_err"], 1e-12)
+    assert_close(r["data"], g[name + "_data"], 1e-15)
+    assert_close(O.grid_pdf_with_counts(bounds, g[name + "_pdf_xs"], base, counts), g[name + "_pdf"], 1e-14)
