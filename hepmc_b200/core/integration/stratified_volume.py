@@ -27,15 +27,15 @@ class GridVolumes(Distribution):
         self.default_base_count = default_base_count
         self._grid = None       # device tensor (ndim, 2K+1), created on first device use
         self._host = None       # float64 array (ndim, 2K+1): the authoritative copy until then
+        self._ragged = None     # list of per-axis bounds when the axes have different divisions (host only)
         if bounds is None:
             Distribution.__init__(self, ndim, False)
             if not np.isscalar(divisions):
                 if len(divisions) != ndim:
                     raise RuntimeError("Divisions must be scalar or of length ndim")
-                if len(set(int(k) for k in divisions)) != 1:
-                    raise NotImplementedError("hepmc_b200 grids use the same number of divisions on every axis")
-                divisions = int(divisions[0])
-            self.bounds = [np.linspace(0, 1, divisions + 1) for _ in range(ndim)]
+                self.bounds = [np.linspace(0, 1, int(k) + 1) for k in divisions]
+            else:
+                self.bounds = [np.linspace(0, 1, divisions + 1) for _ in range(ndim)]
         else:
             Distribution.__init__(self, len(bounds), False)
             self.bounds = bounds
@@ -44,14 +44,25 @@ class GridVolumes(Distribution):
     # ---- state ------------------------------------------------------------------
     @property
     def divisions(self):
+        """Bins per axis (an int for the regular grids VEGAS uses, a tuple when the axes differ)."""
+        if self._ragged is not None:
+            return tuple(len(b) - 1 for b in self._ragged)
         return (self._state_host().shape[1] - 1) // 2
 
+    def _shape(self):
+        k = self.divisions
+        return tuple(k) if isinstance(k, tuple) else (k,) * self.ndim
+
     def _state_host(self):
+        if self._ragged is not None:
+            raise NotImplementedError("the grid kernels (VEGAS, hepmc_grid_pdf) need the same number of divisions on "
+                                      "every axis; grids with different divisions serve StratifiedMC / pdf / rvs")
         if self._grid is not None:
             self._host = self._grid.cpu().numpy()
         return self._host
 
     def _set_state(self, host):
+        self._ragged = None
         self._host = np.ascontiguousarray(host, dtype=np.float64)
         self._grid = None
         k = (self._host.shape[1] - 1) // 2
@@ -62,6 +73,8 @@ class GridVolumes(Distribution):
 
     def device_grid(self):
         """The (ndim, 2K+1) CUDA tensor the kernels use (authoritative once created)."""
+        if self._ragged is not None:
+            self._state_host()      # raises: the grid kernels need equal divisions on every axis
         if self._grid is None:
             self._grid, _ = _lib.to_device(self._host)
         return self._grid
@@ -71,27 +84,37 @@ class GridVolumes(Distribution):
 
     @property
     def bounds(self):
+        if self._ragged is not None:
+            return [b.copy() for b in self._ragged]
         st = self._state_host()
         k = self.divisions
         return [st[d, :k + 1].copy() for d in range(self.ndim)]
 
     @bounds.setter
     def bounds(self, bounds):
-        b = np.stack([np.asarray(x, dtype=np.float64) for x in bounds])
+        rows = [np.asarray(x, dtype=np.float64) for x in bounds]
+        if len(set(len(r) for r in rows)) > 1:
+            self._ragged = [r.copy() for r in rows]
+            self._host = self._grid = None
+            self.partition_count = float(np.prod([len(r) - 1 for r in rows]))
+            self.total_base_count = (sum(self.base_counts.values()) +
+                                     self.default_base_count * (self.partition_count - len(self.base_counts)))
+            return
+        b = np.stack(rows)
         self._set_state(np.concatenate([b, np.diff(b, axis=1)], axis=1))
 
     @property
     def sizes(self):
+        if self._ragged is not None:
+            return [np.diff(b) for b in self._ragged]
         st = self._state_host()
         k = self.divisions
         return [st[d, k + 1:].copy() for d in range(self.ndim)]
 
     @sizes.setter
     def sizes(self, sizes):
-        s = np.stack([np.asarray(x, dtype=np.float64) for x in sizes])
-        b = np.zeros((s.shape[0], s.shape[1] + 1))          # bounds[d][0] = 0 (App. B2)
-        b[:, 1:] = np.cumsum(s, axis=1)
-        self._set_state(np.concatenate([b, s], axis=1))
+        rows = [np.asarray(x, dtype=np.float64) for x in sizes]
+        self.bounds = [np.concatenate([[0.0], np.cumsum(r)]) for r in rows]   # bounds[d][0] = 0 (App. B2)
 
     # ---- sampling ---------------------------------------------------------------
     def _sample(self, count, want_idx):
@@ -107,8 +130,16 @@ class GridVolumes(Distribution):
                       None, None, _lib.ptr(x), None, _lib.ptr(w), _lib.ptr(idx), None, None, _lib.stream_ptr())
         return x, w, idx
 
+    def _bins_dev(self):
+        dev = _lib.device()
+        return [torch.as_tensor(b, device=dev) for b in self.bounds]
+
     def random_bins(self, count):
         """(ndim, count) uniformly chosen bin indices (stratified_volume.py:104-113)."""
+        if self._ragged is not None:
+            u = engine.uniform_rvs(int(count), self.ndim)
+            ks = torch.as_tensor(self._shape(), device=u.device, dtype=torch.float64)
+            return config.deliver(torch.minimum((u * ks).floor(), ks - 1).to(torch.int64).t().contiguous())
         return config.deliver(self._sample(int(count), True)[2])
 
     def sample_indices(self, indices):
@@ -117,6 +148,10 @@ class GridVolumes(Distribution):
         idx, host = _lib.to_device(indices, dtype=torch.int64)
         n = idx.shape[1]
         u = engine.uniform_rvs(n * self.ndim, 1).reshape(self.ndim, n).contiguous()
+        if self._ragged is not None:
+            b = self._bins_dev()
+            x = torch.stack([b[d][idx[d]] + (b[d][idx[d] + 1] - b[d][idx[d]]) * u[d] for d in range(self.ndim)])
+            return _lib.to_host_like(x, host)
         x = torch.empty((self.ndim, n), dtype=torch.float64, device=idx.device)
         w = torch.empty(n, dtype=torch.float64, device=idx.device)
         io = torch.empty((self.ndim, n), dtype=torch.int64, device=idx.device)
@@ -129,6 +164,11 @@ class GridVolumes(Distribution):
 
     def rvs(self, sample_count):
         """(N, ndim) points distributed like the grid (:124-126)."""
+        if self._ragged is not None:
+            idx = self.random_bins(int(sample_count))
+            x = self.sample_indices(idx)
+            x = x if isinstance(x, torch.Tensor) else torch.as_tensor(x, device=_lib.device())
+            return config.deliver(x.t().contiguous())
         x, _, _ = self._sample(int(sample_count), False)
         return config.deliver(x.t().contiguous())
 
@@ -139,12 +179,12 @@ class GridVolumes(Distribution):
 
     def _cells(self, multiple=1):
         """All bins in np.ndindex order: counts (n_cells,), lower / upper corners (n_cells, ndim)."""
-        k = self.divisions
-        b = np.stack(self.bounds)
-        index = np.stack(np.unravel_index(np.arange(k ** self.ndim), (k,) * self.ndim), axis=1)
+        shape = self._shape()
+        b = self.bounds
+        index = np.stack(np.unravel_index(np.arange(int(np.prod(shape))), shape), axis=1)
         counts = np.full(index.shape[0], int(multiple * self.default_base_count), dtype=np.int64)
         for key, value in self.base_counts.items():
-            counts[np.ravel_multi_index(tuple(int(i) for i in key), (k,) * self.ndim)] = int(multiple * value)
+            counts[np.ravel_multi_index(tuple(int(i) for i in key), shape)] = int(multiple * value)
         lower = np.stack([b[d][index[:, d]] for d in range(self.ndim)], axis=1)
         upper = np.stack([b[d][index[:, d] + 1] for d in range(self.ndim)], axis=1)
         return counts, lower, upper
@@ -188,11 +228,10 @@ class GridVolumes(Distribution):
     def pdf_indices(self, indices):
         """count / total_base_count / volume of the given bins (:67-72)."""
         idx = torch.as_tensor(np.asarray(indices) if not isinstance(indices, torch.Tensor) else indices).cpu().long()
-        st = torch.as_tensor(self._state_host())
-        k = self.divisions
+        sz = [torch.as_tensor(v) for v in self.sizes]
         vols = torch.ones(idx.shape[1], dtype=torch.float64)
         for d in range(self.ndim):
-            vols = vols * st[d, k + 1:][idx[d]]
+            vols = vols * sz[d][idx[d]]
         out = self.default_base_count * self._count_factor(idx) / self.total_base_count / vols
         return out.numpy()
 
@@ -200,6 +239,18 @@ class GridVolumes(Distribution):
         """1 / (K^ndim * bin volume) inside the open unit cube, 0 outside (:74-83)."""
         xs = interpret_array(xs, self.ndim)
         x_dev, host = _lib.to_device(xs)
+        if self._ragged is not None:
+            # different divisions per axis: bin search with torch ops on the device
+            b = self._bins_dev()
+            shape = self._shape()
+            idx = torch.stack([(torch.bucketize(x_dev[:, d].contiguous(), b[d], right=True) - 1).clamp_(0, shape[d] - 1)
+                               for d in range(self.ndim)])
+            vols = torch.ones(x_dev.shape[0], dtype=torch.float64, device=x_dev.device)
+            for d in range(self.ndim):
+                vols = vols * (b[d][idx[d] + 1] - b[d][idx[d]])
+            inside = ((x_dev > 0) & (x_dev < 1)).all(dim=1)
+            out = self.default_base_count * self._count_factor(idx) / self.total_base_count / vols
+            return _lib.to_host_like(torch.where(inside, out, torch.zeros_like(out)), host)
         out = torch.empty(x_dev.shape[0], dtype=torch.float64, device=x_dev.device)
         if x_dev.shape[0]:
             _lib.call("hepmc_grid_pdf", _lib.ptr(self.device_grid()), self.ndim, self.divisions, _lib.ptr(x_dev),

@@ -1198,3 +1198,25 @@ def test_stratified_native():
     vol = H.GridVolumes(ndim=2, divisions=20, default_base_count=500)
     s = H.StratifiedMC(volumes=vol)(H.densities.Camel(2), 2, keep_samples=False)
     assert s.data is None and abs(s.integral - 1.0) < 5 * s.integral_err and s.integral_err < 5e-3
+
+
+def test_grid_volumes_with_different_divisions_per_axis():
+    """GridVolumes(divisions=[...]) (stratified_volume.py:46-51): StratifiedMC, pdf, rvs and the
+    index helpers work through the generic device path; the VEGAS kernels refuse such a grid."""
+    H.seed(23)
+    vol = H.GridVolumes(ndim=2, divisions=[3, 5], default_base_count=40, base_counts={(1, 2): 400})
+    assert vol.divisions == (3, 5) and vol.partition_count == 15 and vol.total_base_count == 14 * 40 + 400
+    s = H.StratifiedMC(volumes=vol)(H.densities.Camel(2), 50)
+    assert s.sub_sizes == [2000] * 7 + [20000] + [2000] * 7 and abs(s.integral - 1.0) < 5 * s.integral_err
+    xs = np.random.default_rng(0).random((500, 2))
+    bounds = [np.linspace(0, 1, 4), np.linspace(0, 1, 6)]
+    assert_close(vol.pdf(xs), O.grid_pdf_with_counts(bounds, xs, 40, {(1, 2): 400}), 1e-13)
+    assert vol.pdf(np.array([[1.5, 0.5]]))[0] == 0.0
+    bins = vol.random_bins(20000)
+    assert bins.shape == (2, 20000) and bins[0].max() == 2 and bins[1].max() == 4 and bins.min() == 0
+    pts = vol.sample_indices(bins)
+    assert pts.shape == (2, 20000) and np.all(np.floor(pts[0] * 3) == bins[0]) and np.all(np.floor(pts[1] * 5) == bins[1])
+    r = vol.rvs(30000)
+    assert r.shape == (30000, 2) and abs(r.mean() - 0.5) < 0.01
+    with pytest.raises(NotImplementedError):
+        vol.device_grid()
