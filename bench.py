@@ -205,7 +205,8 @@ def run_b200(args):
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record()
         _lib.call("hepmc_vegas_sample", ctypes.byref(blk), _lib.ptr(grid), NDIM, DIVISIONS, n_local, first, chunk,
-                  1234, 1000 + i, None, None, None, None, None, None, _lib.ptr(sp), _lib.ptr(hp), _lib.stream_ptr())
+                  1234, 1000 + i, rng.mode_code(), None, None, None, None, None, None, _lib.ptr(sp), _lib.ptr(hp),
+                  _lib.stream_ptr())
         k1.record()
         torch.cuda.synchronize()
         if i >= 3:

@@ -54,16 +54,16 @@ SIGNATURES = {
     "hepmc_fp64_probe": (_int, [_i64, ctypes.POINTER(_dbl), ctypes.POINTER(_dbl), _vp]),
     "hepmc_density_eval": (_int, [_dens_p, _int, _vp, _i64, _vp, _vp]),
     "hepmc_default_chunk": (_i64, [_i64]),
-    "hepmc_plain_mc_sample": (_int, [_dens_p, _i64, _i64, _i64, _u64, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "hepmc_plain_mc_sample": (_int, [_dens_p, _i64, _i64, _i64, _u64, _u32, _int, _vp, _vp, _vp, _vp, _vp]),
     "hepmc_reduce_stats": (_int, [_vp, ctypes.POINTER(_i64), _int, _vp, _vp]),
     "hepmc_stats_partials": (_int, [_vp, _vp, _dbl, _i64, _i64, _vp, _vp]),
-    "hepmc_vegas_sample": (_int, [_dens_p, _vp, _int, _int, _i64, _i64, _i64, _u64, _u32,
+    "hepmc_vegas_sample": (_int, [_dens_p, _vp, _int, _int, _i64, _i64, _i64, _u64, _u32, _int,
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hepmc_vegas_accumulate": (_int, [_vp, _vp, _vp, _int, _int, _i64, _i64, _vp, _vp, _vp]),
     "hepmc_reduce_hist": (_int, [_vp, ctypes.POINTER(_i64), _int, _int, _vp, _vp]),
     "hepmc_vegas_update_grid": (_int, [_vp, _vp, _int, _vp, _int, _int, _dbl, _int, _vp, _vp]),
     "hepmc_vegas_workspace_bytes": (_i64, [_int, _int, _i64]),
-    "hepmc_vegas_integrate": (_int, [_dens_p, _vp, _int, _int, _i64, _int, _dbl, _u64, _u32,
+    "hepmc_vegas_integrate": (_int, [_dens_p, _vp, _int, _int, _i64, _int, _dbl, _u64, _u32, _int,
                                      _vp, _vp, _i64, _vp]),
     "hepmc_grid_pdf": (_int, [_vp, _int, _int, _vp, _i64, _vp, _vp]),
     "hepmc_multichannel_sample": (_int, [_dens_p, _vp, _int, _int, _i64, _i64, _i64, _u64, _u32,

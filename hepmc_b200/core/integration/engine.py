@@ -29,7 +29,7 @@ def uniform_rvs(n, ndim, stream_id=None):
     sid = rng.next_stream() if stream_id is None else stream_id
     blk = none_block(ndim)
     _lib.call("hepmc_plain_mc_sample", ctypes.byref(blk), n, 0, _lib.default_chunk(n), rng.get_seed(), sid,
-              None, _lib.ptr(out), None, None, _lib.stream_ptr())
+              rng.MODES["u52r10"], None, _lib.ptr(out), None, None, _lib.stream_ptr())
     return out
 
 

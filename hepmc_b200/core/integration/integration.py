@@ -61,6 +61,7 @@ class PlainMC(object):
         sid = rng.next_stream()
         if n_local:
             _lib.call("hepmc_plain_mc_sample", ctypes.byref(blk), n_local, first, chunk, rng.get_seed(), sid,
+                      rng.mode_code(),
                       _lib.ptr(u_replay), _lib.ptr(data), _lib.ptr(fvals), _lib.ptr(partials), _lib.stream_ptr())
         if not fused:
             fvals = engine.call_integrand(fn, [data[:, d] for d in range(self.ndim)])

@@ -126,7 +126,7 @@ class GridVolumes(Distribution):
         if count:
             blk = engine.none_block(self.ndim)
             _lib.call("hepmc_vegas_sample", ctypes.byref(blk), _lib.ptr(self.device_grid()), self.ndim, k,
-                      count, 0, _lib.default_chunk(count), rng.get_seed(), rng.next_stream(),
+                      count, 0, _lib.default_chunk(count), rng.get_seed(), rng.next_stream(), rng.mode_code(),
                       None, None, _lib.ptr(x), None, _lib.ptr(w), _lib.ptr(idx), None, None, _lib.stream_ptr())
         return x, w, idx
 
@@ -158,7 +158,7 @@ class GridVolumes(Distribution):
         if n:
             blk = engine.none_block(self.ndim)
             _lib.call("hepmc_vegas_sample", ctypes.byref(blk), _lib.ptr(self.device_grid()), self.ndim,
-                      self.divisions, n, 0, _lib.default_chunk(n), 0, 0, _lib.ptr(idx), _lib.ptr(u),
+                      self.divisions, n, 0, _lib.default_chunk(n), 0, 0, 0, _lib.ptr(idx), _lib.ptr(u),
                       _lib.ptr(x), None, _lib.ptr(w), _lib.ptr(io), None, None, _lib.stream_ptr())
         return _lib.to_host_like(x, host)
 

@@ -94,7 +94,7 @@ class VegasMC(object):
             nbytes = int(_lib.load().hepmc_vegas_workspace_bytes(ndim, K, n_total))
             work = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=dev)
             _lib.call("hepmc_vegas_integrate", ctypes.byref(blk), _lib.ptr(grid), ndim, K, n_total, int(iterations),
-                      float(self.c), rng.get_seed(), rng.next_stream(iterations), _lib.ptr(est_var), _lib.ptr(work),
+                      float(self.c), rng.get_seed(), rng.next_stream(iterations), rng.mode_code(), _lib.ptr(est_var), _lib.ptr(work),
                       nbytes, _lib.stream_ptr())
             return self._combine(est_var, n_total, iterations, chi, None)
         chunk = _lib.default_chunk(n_total)
@@ -131,7 +131,7 @@ class VegasMC(object):
             idx = torch.empty((ndim, n_local), dtype=torch.int64, device=dev) if not fused else None
             if n_local:
                 _lib.call("hepmc_vegas_sample", ctypes.byref(blk), _lib.ptr(grid), ndim, K, n_local, first, chunk,
-                          seed, sid0 + j,
+                          seed, sid0 + j, rng.mode_code(),
                           _lib.ptr(idx_tape[j]) if idx_tape is not None else None,
                           _lib.ptr(u_tape[j]) if u_tape is not None else None,
                           _lib.ptr(x), _lib.ptr(f), _lib.ptr(w), _lib.ptr(idx),

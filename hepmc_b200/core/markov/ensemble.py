@@ -130,7 +130,7 @@ def _step_draws(n_chains, n_uniform, first_chain, stream_id, dev):
     out = torch.empty((n_chains, n_uniform), dtype=torch.float64, device=dev)
     blk = none_block(n_uniform)
     _lib.call("hepmc_plain_mc_sample", ctypes.byref(blk), n_chains, int(first_chain), _lib.default_chunk(n_chains),
-              rng.get_seed(), int(stream_id), None, _lib.ptr(out), None, None, _lib.stream_ptr())
+              rng.get_seed(), int(stream_id), rng.MODES["u52r10"], None, _lib.ptr(out), None, None, _lib.stream_ptr())
     return out
 
 

@@ -278,18 +278,33 @@ static int check_sample_common(const char* who, int ndim, int K, int64_t n, int6
 #define HEPMC_GENERIC_CASE(KIND)                                                                            \
     case KIND:                                                                                              \
         if (vegas) {                                                                                        \
-            HEPMC_CUDA(cudaFuncSetAttribute(vegas_sample_kernel<KIND, 0, false>,                            \
+            HEPMC_CUDA(cudaFuncSetAttribute(vegas_sample_kernel<KIND>,                                      \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-            vegas_sample_kernel<KIND, 0, false><<<blocks, threads, smem, st>>>(dens, a);                    \
+            vegas_sample_kernel<KIND><<<blocks, threads, smem, st>>>(dens, a);                              \
         } else {                                                                                            \
             plain_sample_kernel<KIND, 0, false><<<blocks, 256, 0, st>>>(dens, a);                           \
         }                                                                                                   \
         break;
 
-// fast = native RNG: compile-time (kind, ndim) instance when one exists (ndim <= 16), with or
+static int max_optin_smem() {
+    int dev = 0, maxs = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&maxs, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return maxs;
+}
+
+// fast = native RNG: compile-time (kind, ndim, rng mode) instance when one exists (ndim <= 16), with or
 // without per-point outputs; else the generic kernel (runtime ndim, replay tapes).
 static int launch_sample(bool vegas, bool fast, const Dens& dens, const SampleArgs& a, unsigned blocks, int threads,
                          size_t smem, cudaStream_t st) {
+    if (fast && vegas) {
+        // the throughput kernel has its own shared-memory layout (256 threads); huge grids take the generic one
+        const size_t fs = vegas_fast_smem_bytes(a.ndim, a.K, 256);
+        const bool camel = dens.kind == HEPMC_CAMEL || dens.kind == HEPMC_UCAMEL;
+        if (a.ndim > 16 || (int64_t)fs > (int64_t)max_optin_smem() || a.chunk % 256 != 0 ||
+            (camel && !camel_uniform_means(dens))) fast = false;
+        else smem = fs;
+    }
     if (fast) {
         const bool out = a.x_out || a.f_out || a.w_out || a.idx_out;
         int e = -100;
@@ -332,7 +347,7 @@ int64_t hepmc_default_chunk(int64_t n_total) {
 }
 
 int hepmc_plain_mc_sample(const hepmc_density_t* dens, int64_t n, int64_t first_index, int64_t chunk,
-                          uint64_t seed, uint32_t stream_id, const double* u_replay_dev,
+                          uint64_t seed, uint32_t stream_id, int rng_mode, const double* u_replay_dev,
                           double* data_dev, double* f_dev, double* partials_dev, void* stream) {
     HEPMC_REQUIRE(dens != nullptr, HEPMC_E_ARG, "hepmc_plain_mc_sample: dens is NULL");
     int e = check_sample_common("hepmc_plain_mc_sample", dens->ndim, 1, n, first_index, chunk,
@@ -341,10 +356,13 @@ int hepmc_plain_mc_sample(const hepmc_density_t* dens, int64_t n, int64_t first_
     HEPMC_REQUIRE(dens->kind >= HEPMC_CAMEL && dens->kind <= HEPMC_NONE, HEPMC_E_ARG, "bad density kind %d", dens->kind);
     HEPMC_REQUIRE(dens->kind == HEPMC_NONE || partials_dev, HEPMC_E_ARG, "hepmc_plain_mc_sample: partials_dev is NULL");
     HEPMC_REQUIRE(dens->kind != HEPMC_NONE || data_dev, HEPMC_E_ARG, "hepmc_plain_mc_sample: nothing to do");
+    HEPMC_REQUIRE(rng_mode >= 0 && rng_mode < HEPMC_RNG_MODES, HEPMC_E_ARG, "hepmc_plain_mc_sample: unknown rng_mode %d", rng_mode);
     if (n == 0) return 0;
     SampleArgs a{};
     a.ndim = dens->ndim; a.K = 1; a.n = n; a.first_index = first_index; a.chunk = chunk;
     a.seed = seed; a.stream_id = stream_id; a.u_replay = u_replay_dev;
+    a.rng_mode = rng_mode;
+    a.keys = philox_expand(seed);
     a.x_out = data_dev; a.f_out = f_dev; a.stats_partials = partials_dev;
     const int64_t blocks = (n + chunk - 1) / chunk;
     const bool fast = !u_replay_dev;   // native draws: templated instance, with outputs if any pointer is given
@@ -390,7 +408,7 @@ int hepmc_reduce_hist(const double* rows_dev, const int64_t* row_begin_host, int
 }
 
 int hepmc_vegas_sample(const hepmc_density_t* dens, const double* grid_dev, int ndim, int divisions,
-                       int64_t n, int64_t first_index, int64_t chunk, uint64_t seed, uint32_t stream_id,
+                       int64_t n, int64_t first_index, int64_t chunk, uint64_t seed, uint32_t stream_id, int rng_mode,
                        const int64_t* idx_replay_dev, const double* u_replay_dev,
                        double* x_dev, double* f_dev, double* w_dev, int64_t* idx_dev,
                        double* stats_partials_dev, double* hist_partials_dev, void* stream) {
@@ -400,6 +418,7 @@ int hepmc_vegas_sample(const hepmc_density_t* dens, const double* grid_dev, int 
     HEPMC_REQUIRE(dens->kind >= HEPMC_CAMEL && dens->kind <= HEPMC_NONE, HEPMC_E_ARG, "bad density kind %d", dens->kind);
     HEPMC_REQUIRE(dens->kind == HEPMC_NONE || dens->ndim == ndim, HEPMC_E_ARG,
                   "hepmc_vegas_sample: density ndim %d != grid ndim %d", dens->ndim, ndim);
+    HEPMC_REQUIRE(rng_mode >= 0 && rng_mode < HEPMC_RNG_MODES, HEPMC_E_ARG, "hepmc_vegas_sample: unknown rng_mode %d", rng_mode);
     HEPMC_REQUIRE((idx_replay_dev == nullptr) == (u_replay_dev == nullptr), HEPMC_E_ARG,
                   "hepmc_vegas_sample: replay needs both idx and u tapes");
     const bool fused = dens->kind != HEPMC_NONE;
@@ -419,6 +438,9 @@ int hepmc_vegas_sample(const hepmc_density_t* dens, const double* grid_dev, int 
     a.x_out = x_dev; a.f_out = f_dev; a.w_out = w_dev; a.idx_out = idx_dev;
     a.stats_partials = stats_partials_dev; a.hist_partials = hist_partials_dev;
     a.kpow = pow((double)divisions, (double)ndim);
+    a.rng_mode = rng_mode;
+    a.keys = philox_expand(seed);
+    set_camel_centre(a, *dens);
     const int64_t blocks = (n + chunk - 1) / chunk;
     const bool fast = !u_replay_dev;   // native draws: templated instance, with outputs if any pointer is given
     int e2 = launch_sample(true, fast, *dens, a, (unsigned)blocks, threads, smem, as_stream(stream));
@@ -478,7 +500,7 @@ int64_t hepmc_vegas_workspace_bytes(int ndim, int divisions, int64_t n) {
 }
 
 int hepmc_vegas_integrate(const hepmc_density_t* dens, double* grid_dev, int ndim, int divisions,
-                          int64_t n, int iterations, double c, uint64_t seed, uint32_t stream_id0,
+                          int64_t n, int iterations, double c, uint64_t seed, uint32_t stream_id0, int rng_mode,
                           double* est_var_dev, void* workspace_dev, int64_t workspace_bytes,
                           void* stream) {
     HEPMC_REQUIRE(dens && grid_dev && est_var_dev && workspace_dev, HEPMC_E_ARG, "hepmc_vegas_integrate: NULL buffer");
@@ -497,7 +519,7 @@ int hepmc_vegas_integrate(const hepmc_density_t* dens, double* grid_dev, int ndi
     int64_t begin[HEPMC_N_SLOTS + 1];
     slot_ranges(nc, begin);
     for (int j = 0; j < iterations; ++j) {
-        int e = hepmc_vegas_sample(dens, grid_dev, ndim, divisions, n, 0, chunk, seed, stream_id0 + (uint32_t)j,
+        int e = hepmc_vegas_sample(dens, grid_dev, ndim, divisions, n, 0, chunk, seed, stream_id0 + (uint32_t)j, rng_mode,
                                    nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats_p, hist_p, stream);
         if (e) return e;
         e = hepmc_reduce_stats(stats_p, begin, HEPMC_N_SLOTS, slot_stats, stream);

@@ -4,6 +4,7 @@
 // per-point outputs -- keep_samples=True, the reference's default -- per (kind, ndim), and
 // sample-only instances (kind NONE) for user integrands).
 #pragma once
+#include <type_traits>
 #include "density.cuh"
 
 namespace hepmc {
@@ -34,65 +35,31 @@ struct SampleArgs {
     double* stats_partials;
     double* hist_partials;
     double kpow;
+    PhiloxKey keys;  // round keys of `seed`, expanded on the host: constant-bank operands of the Philox rounds
+    double camel_c, camel_2h, camel_h2;  // centred camel of the throughput kernel (vegas_fast.cuh): (a+b)/2, b-a, n((b-a)/2)^2
+    int rng_mode;  // HEPMC_RNG_*: bits per draw and Philox rounds of the native generator (hepmc_set_rng_mode)
     // two-kernel path inputs (accumulate)
     const double* f_in;
     const double* w_in;
     const int64_t* idx_in;
 };
 
-// lane L < ngrp*ndim: axis d = L % ndim, walks points grp, grp+ngrp, ... of the warp tile.
+// Histogram phase of a warp tile of 32 points, runtime geometry (generic kernels).  Lane L: axis
+// d = L % ndim, group g = L / ndim; group g walks the points g*nupd .. g*nupd + nupd - 1 in order,
+// nupd = 32 / ngrp rounded up to 4, 8, 16 or 32.  The SAME assignment as the throughput kernel
+// (HistGeom in vegas_fast.cuh), so fused, two-kernel and replay paths add in the same order.
 __device__ __forceinline__ void warp_hist_update(double* hist_w, const double* wf_w, const uint32_t* bins_w,
                                                  int ndim, int lane) {
     const int ngrp = 32 / ndim;
-    if (lane < ngrp * ndim) {
-        const int d = lane % ndim, grp = lane / ndim;
+    const int need = (32 + ngrp - 1) / ngrp;
+    const int nupd = need <= 4 ? 4 : need <= 8 ? 8 : need <= 16 ? 16 : 32;
+    const int d = lane % ndim, grp = lane / ndim;
+    if (grp < 32 / nupd) {
         const int word = d >> 2, shift = 8 * (d & 3);
-        for (int p = grp; p < 32; p += ngrp) {
+        for (int p = grp * nupd; p < (grp + 1) * nupd; ++p) {
             const double v = wf_w[p];
             const uint32_t bin = (bins_w[p * kBinWords + word] >> shift) & 0xffu;
             hist_w[bin * 32 + lane] += v;
-        }
-    }
-}
-
-#ifndef HEPMC_HIST_PAIR
-#define HEPMC_HIST_PAIR 0
-#endif
-template <int NDIM>
-__device__ __forceinline__ void warp_hist_update_n(double* hist_w, const double* wf_w, const uint32_t* bins_w,
-                                                   int lane) {
-    constexpr int ngrp = 32 / NDIM;
-    constexpr int NUPD = (32 + ngrp - 1) / ngrp;  // updates per lane (points grp, grp+ngrp, ...)
-    if (lane < ngrp * NDIM) {
-        const int d = lane % NDIM, grp = lane / NDIM;
-        const int word = d >> 2, shift = 8 * (d & 3);
-        const uint32_t* bw = bins_w + grp * kBinWords + word;
-        const double* wv = wf_w + grp;
-        double* hcol = hist_w + lane;
-        if constexpr (HEPMC_HIST_PAIR && (32 % ngrp == 0) && (NUPD % 2 == 0)) {
-            // two read-modify-writes in flight: both column entries are loaded before the first
-            // add; if the two bins coincide the second add takes the first result (same order of
-            // additions as the sequential loop, so results are bit-identical)
-#pragma unroll
-            for (int i = 0; i < NUPD; i += 2) {
-                const double v0 = wv[i * ngrp], v1 = wv[(i + 1) * ngrp];
-                const uint32_t b0 = (bw[i * ngrp * kBinWords] >> shift) & 0xffu;
-                const uint32_t b1 = (bw[(i + 1) * ngrp * kBinWords] >> shift) & 0xffu;
-                const double h0 = hcol[b0 * 32], h1 = hcol[b1 * 32];
-                const double t0 = h0 + v0;
-                const double t1 = (b1 == b0 ? t0 : h1) + v1;
-                hcol[b0 * 32] = t0;
-                hcol[b1 * 32] = t1;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < NUPD; ++i) {
-                if (grp + i * ngrp < 32) {
-                    const double v = wv[i * ngrp];
-                    const uint32_t bin = (bw[i * ngrp * kBinWords] >> shift) & 0xffu;
-                    hcol[bin * 32] += v;
-                }
-            }
         }
     }
 }
@@ -107,6 +74,13 @@ __device__ __forceinline__ void block_hist_flush(const double* s_hist, int ndim,
             for (int g = 0; g < ngrp; ++g) s += s_hist[(w * K + k) * 32 + g * ndim + d];
         out_row[j] = s;
     }
+}
+
+inline void set_camel_centre(SampleArgs& a, const Dens& p) {
+    const double h = 0.5 * (p.b[0] - p.a[0]);
+    a.camel_c = 0.5 * (p.a[0] + p.b[0]);
+    a.camel_2h = 2.0 * h;
+    a.camel_h2 = (double)p.ndim * h * h;
 }
 
 struct SmemLayout {
@@ -137,24 +111,59 @@ __device__ __forceinline__ SmemLayout carve(double* base, int ndim, int K, int n
     return s;
 }
 
-// ------------------------------------------------------------------ VEGAS sample (+ fused integrand)
+// ------------------------------------------------------------------ draws of the native generator
+// modes: enum hepmc_rng_mode (include/hepmc_b200.h)
+
+template <int R>
+__device__ __forceinline__ U4 philox4x32_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKey& key) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.k0[r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ key.k1[r];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    return U4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ U4 philox4x32_mode(int mode, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              const PhiloxKey& key) {
+    return mode == HEPMC_RNG_U32_R7 ? philox4x32_r<7>(c0, c1, c2, c3, key) : philox4x32_r<10>(c0, c1, c2, c3, key);
+}
+
+// 32 random bits -> uniform (w + 1/2) 2^-32 in (0,1), exact: as_double(0x41300000 : w) = 2^20 + w 2^-32,
+// minus (2^20 - 2^-33).  Oracle: hepmc_oracle.u32.
+__device__ __forceinline__ double u32(uint32_t w) {
+    return __hiloint2double(0x41300000, (int)w) - 1048575.99999999988358467817306518554687500;
+}
+
+// 32 random bits -> (bin, offset): t = K*w; bin = floor(t / 2^32); offset = (t mod 2^32 + 1/2) 2^-32.
+// Same joint law as randint + rand (stratified_volume.py:111,121) at 32-bit resolution: bin
+// probabilities differ from 1/K by at most 2^-32.  Oracle: hepmc_oracle.vegas_bin_frac32.
+__device__ __forceinline__ void bin_frac32(uint32_t w, uint32_t K, uint32_t& bin, double& frac) {
+    const uint64_t t = (uint64_t)K * w;
+    bin = (uint32_t)(t >> 32);
+    frac = u32((uint32_t)t);
+}
+
+// ------------------------------------------------------------------ VEGAS sample, generic instance
+// Runtime dimensionality, replay tapes, all per-point outputs: parity runs and shapes without a
+// throughput instance (ndim > 16).  The throughput kernel is vegas_fast_kernel (vegas_fast.cuh).
 // KIND: integrand fused into the kernel (HEPMC_NONE: sample/weight only).
-// NDIM_T: compile-time dimensionality (0 = runtime) -- full unroll, static bin packing.
-// FAST: native RNG, no per-point outputs (the throughput path); otherwise replay tapes and
-//       x / f / w / idx outputs are honoured through warp-uniform runtime flags.
 // Shared grid layout: per axis K entries of (bound_k, size_k) as double2 -> one LDS.128.
-template <int KIND, int NDIM_T, bool FAST, bool OUT = !FAST>
-__global__ void __launch_bounds__(256, FAST ? kFastMinBlocks : 1) vegas_sample_kernel(const __grid_constant__ Dens dens,
-                                                           const __grid_constant__ SampleArgs a) {
+template <int KIND>
+__global__ void __launch_bounds__(256, 1) vegas_sample_kernel(const __grid_constant__ Dens dens,
+                                                              const __grid_constant__ SampleArgs a) {
     extern __shared__ double smem_raw[];
-    const int ndim = NDIM_T ? NDIM_T : a.ndim;
+    const int ndim = a.ndim;
     const int K = a.K;
     const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SmemLayout s = carve(smem_raw, ndim, K, nw);
     constexpr bool fused = KIND != HEPMC_NONE;
-    // points per thread and loop trip: two independent points in flight on the throughput path
-    // (more ILP against the dependent Philox / FP64 chains); identical results either way
-    constexpr int PPI = FAST ? kFastPPI : 1;
     double2* s_grid2 = reinterpret_cast<double2*>(s.grid);  // [ndim][K] (bound, size); 2K <= 2K+1 doubles per axis
 
     for (int i = threadIdx.x; i < ndim * K; i += blockDim.x) {
@@ -171,105 +180,77 @@ __global__ void __launch_bounds__(256, FAST ? kFastMinBlocks : 1) vegas_sample_k
     uint32_t* bins_w = s.bins + warp * 32 * kBinWords * kMaxPPI;
 
     const PhiloxKey key = philox_expand(a.seed);
-    const bool replay = !FAST && a.u_replay != nullptr;
+    const bool replay = a.u_replay != nullptr;
+    const bool w32 = a.rng_mode != HEPMC_RNG_U52_R10;
+    const int per = w32 ? 4 : 2;                       // axes served by one Philox call
+    const int ncalls = (ndim + per - 1) / per;
     const int64_t chunk0 = (int64_t)blockIdx.x * a.chunk;
     const int ppt = (int)(a.chunk / blockDim.x);
-    const int ncalls = NDIM_T ? (NDIM_T + 1) / 2 : (ndim + 1) >> 1;
-    constexpr int NPACK = NDIM_T ? (NDIM_T + 3) / 4 : kBinWords - 1;
+    constexpr int NPACK = kBinWords - 1;
     ShiftedAcc acc;
     acc.init();
 
-    // one sample point: draws -> grid map -> integrand -> weight; returns f*w and the packed bins
-    auto point = [&](int64_t li, double& wf, uint32_t (&packed)[NPACK]) {
-        const uint64_t g = (uint64_t)(a.first_index + li);
-        const bool ok = li < a.n;   // the FAST loop also runs the padding points of the last chunk: they store nothing
-        double* xp = (OUT && a.x_out && ok) ? a.x_out + li : nullptr;
-        int64_t* ip = (OUT && a.idx_out && ok) ? a.idx_out + li : nullptr;
-        PdfAcc pa;
-        pa.init();
-        double w = 1.0;
+    for (int it = 0; it < ppt; ++it) {
+        const int64_t li = chunk0 + (int64_t)it * blockDim.x + threadIdx.x;
+        const bool valid = li < a.n;
+        double wf = 0.0;
+        uint32_t packed[NPACK];
 #pragma unroll
-        for (int call = 0; call < ncalls; ++call) {
-            U4 r{0u, 0u, 0u, 0u};
-            if (FAST || !replay) r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)call, a.stream_id, key);
+        for (int q = 0; q < NPACK; ++q) packed[q] = 0u;
+        if (valid) {
+            const uint64_t g = (uint64_t)(a.first_index + li);
+            double* xp = a.x_out ? a.x_out + li : nullptr;
+            int64_t* ip = a.idx_out ? a.idx_out + li : nullptr;
+            PdfAcc pa;
+            pa.init();
+            double w = 1.0;
+            for (int call = 0; call < ncalls; ++call) {
+                U4 r{0u, 0u, 0u, 0u};
+                if (!replay) r = philox4x32_mode(a.rng_mode, (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)call, a.stream_id, key);
+                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int d = 2 * call + h;
-                if (d < ndim) {
-                    uint32_t bin;
-                    double frac;
-                    if (!FAST && replay) {
-                        bin = (uint32_t)a.idx_replay[(int64_t)d * a.n + li];
-                        frac = a.u_replay[(int64_t)d * a.n + li];
-                    } else {
-                        bin_frac(h ? r.z : r.x, h ? r.w : r.y, (uint32_t)K, bin, frac);
-                    }
-                    const double2 bs = s_grid2[d * K + bin];
-                    const double x = fma(bs.y, frac, bs.x);  // stratified_volume.py:119-121
-                    w *= bs.y;                               // vegas.py:69-70
-                    if constexpr (fused) pdf_acc_dim<KIND, 1>(dens, pa, d, x);
-                    if constexpr (NDIM_T != 0) {
-                        packed[d >> 2] |= bin << (8 * (d & 3));
-                    } else {
+                for (int h = 0; h < 4; ++h) {
+                    const int d = per * call + h;
+                    if (h < per && d < ndim) {
+                        uint32_t bin;
+                        double frac;
+                        if (replay) {
+                            bin = (uint32_t)a.idx_replay[(int64_t)d * a.n + li];
+                            frac = a.u_replay[(int64_t)d * a.n + li];
+                        } else if (w32) {
+                            bin_frac32(rw[h], (uint32_t)K, bin, frac);
+                        } else {
+                            bin_frac(rw[(2 * h) & 3], rw[(2 * h + 1) & 3], (uint32_t)K, bin, frac);
+                        }
+                        const double2 bs = s_grid2[d * K + bin];
+                        const double x = fma(bs.y, frac, bs.x);  // stratified_volume.py:119-121
+                        w *= bs.y;                               // vegas.py:69-70
+                        if constexpr (fused) pdf_acc_dim<KIND, 1>(dens, pa, d, x);
 #pragma unroll
                         for (int q = 0; q < NPACK; ++q)
                             if (q == (d >> 2)) packed[q] |= bin << (8 * (d & 3));
-                    }
-                    if constexpr (OUT) {
-                        // dim-major outputs: running pointers (one 64-bit add per axis instead of a
-                        // 64-bit multiply-add per store)
+                        // dim-major outputs: running pointers
                         if (xp) { *xp = x; xp += a.n; }
                         if (ip) { *ip = (int64_t)bin; ip += a.n; }
                     }
                 }
             }
-        }
-        w *= a.kpow;  // vegas.py:72 (partition_count evaluated in floating point, App. B1)
-        if constexpr (OUT) {
-            if (a.w_out && ok) a.w_out[li] = w;
-        }
-        if constexpr (fused) {
-            const double f = pdf_acc_finish<KIND>(dens, pa);
-            wf = f * w;  // vegas.py:104
-            if constexpr (OUT) {
-                if (a.f_out && ok) a.f_out[li] = f;
-            }
-        }
-    };
-
-    for (int it = 0; it < ppt; it += PPI) {
-        double wf[PPI];
-        uint32_t packed[PPI][NPACK];
-        bool valid[PPI];
-#pragma unroll
-        for (int u = 0; u < PPI; ++u) {
-            const int64_t li = chunk0 + (int64_t)(it + u) * blockDim.x + threadIdx.x;
-            valid[u] = li < a.n;
-            wf[u] = 0.0;
-#pragma unroll
-            for (int q = 0; q < NPACK; ++q) packed[u][q] = 0u;
-            if constexpr (FAST) {
-                point(li, wf[u], packed[u]);  // branch-free: out-of-range points touch no memory and are masked below
-            } else {
-                if (valid[u]) point(li, wf[u], packed[u]);
+            w *= a.kpow;  // vegas.py:72 (partition_count evaluated in floating point, App. B1)
+            if (a.w_out) a.w_out[li] = w;
+            if constexpr (fused) {
+                const double f = pdf_acc_finish<KIND>(dens, pa);
+                wf = f * w;  // vegas.py:104
+                if (a.f_out) a.f_out[li] = f;
+                acc.add(wf);
             }
         }
         if constexpr (fused) {
+            wf_w[lane] = wf;
 #pragma unroll
-            for (int u = 0; u < PPI; ++u) {
-                if (valid[u]) acc.add(wf[u]);
-                else wf[u] = 0.0;
-                wf_w[u * 32 + lane] = wf[u];
-#pragma unroll
-                for (int q = 0; q < NPACK; ++q)
-                    if (q * 4 < ndim) bins_w[(u * 32 + lane) * kBinWords + q] = packed[u][q];
-            }
+            for (int q = 0; q < NPACK; ++q)
+                if (q * 4 < ndim) bins_w[lane * kBinWords + q] = packed[q];
             __syncwarp();
-#pragma unroll
-            for (int u = 0; u < PPI; ++u) {
-                if constexpr (NDIM_T != 0) warp_hist_update_n<NDIM_T>(hist_w, wf_w + u * 32, bins_w + u * 32 * kBinWords, lane);
-                else warp_hist_update(hist_w, wf_w + u * 32, bins_w + u * 32 * kBinWords, ndim, lane);
-            }
+            warp_hist_update(hist_w, wf_w, bins_w, ndim, lane);
             __syncwarp();
         }
     }
@@ -289,7 +270,9 @@ __global__ void __launch_bounds__(256, FAST ? kFastMinBlocks : 1) vegas_sample_k
 }
 
 // ------------------------------------------------------------------ plain MC
-template <int KIND, int NDIM_T, bool FAST, bool OUT = !FAST>
+// NDIM_T: compile-time dimensionality (0 = runtime).  FAST: native RNG only, RNG = its compile-time
+// mode; otherwise replay tapes and the runtime mode a.rng_mode are honoured.
+template <int KIND, int NDIM_T, bool FAST, bool OUT = !FAST, int RNG = HEPMC_RNG_U52_R10>
 __global__ void __launch_bounds__(256) plain_sample_kernel(const __grid_constant__ Dens dens,
                                                            const __grid_constant__ SampleArgs a) {
     __shared__ Stats s_stats[8];
@@ -298,9 +281,13 @@ __global__ void __launch_bounds__(256) plain_sample_kernel(const __grid_constant
     constexpr bool fused = KIND != HEPMC_NONE;
     const PhiloxKey key = philox_expand(a.seed);
     const bool replay = !FAST && a.u_replay != nullptr;
+    const int mode = FAST ? RNG : a.rng_mode;
+    const bool w32 = mode != HEPMC_RNG_U52_R10;
+    constexpr int PERMAX = 4;
+    const int per = w32 ? 4 : 2;
     const int64_t chunk0 = (int64_t)blockIdx.x * a.chunk;
     const int ppt = (int)(a.chunk / blockDim.x);
-    const int ncalls = NDIM_T ? (NDIM_T + 1) / 2 : (ndim + 1) >> 1;
+    const int ncalls = (ndim + per - 1) / per;
     ShiftedAcc acc;
     acc.init();
     for (int it = 0; it < ppt; ++it) {
@@ -312,26 +299,33 @@ __global__ void __launch_bounds__(256) plain_sample_kernel(const __grid_constant
         double xrow[NDIM_T ? NDIM_T : 1];
 #pragma unroll
         for (int call = 0; call < ncalls; ++call) {
-            U4 r{0u, 0u, 0u, 0u};
-            if (FAST || !replay) r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)call, a.stream_id, key);
+            {
+                U4 r{0u, 0u, 0u, 0u};
+                if (FAST || !replay) {
+                    if constexpr (FAST) r = philox4x32_r<(RNG == HEPMC_RNG_U32_R7 ? 7 : 10)>((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)call, a.stream_id, key);
+                    else r = philox4x32_mode(mode, (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)call, a.stream_id, key);
+                }
+                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int d = 2 * call + h;
-                if (d < ndim) {
-                    double x;
-                    if (!FAST && replay) x = a.u_replay[li * ndim + d];
-                    else x = u52(h ? r.z : r.x, h ? r.w : r.y);
-                    // native draws lie strictly inside (0,1); replayed ones get the full check
-                    if constexpr (fused) {
-                        if constexpr (FAST) pdf_acc_dim<KIND, 0>(dens, pa, d, x);
-                        else pdf_acc_dim<KIND, 2>(dens, pa, d, x);
-                    }
-                    if constexpr (OUT) {
-                        // (N, ndim) row-major, integration.py:45.  Compile-time ndim: the row is staged in
-                        // registers and leaves as 256- / 128-bit stores (one contiguous 8 ndim byte run per
-                        // thread); scalar stores of a 128-byte-strided row reach a third of the bandwidth.
-                        if constexpr (NDIM_T != 0) xrow[d] = x;
-                        else if (a.x_out) a.x_out[li * ndim + d] = x;
+                for (int h = 0; h < PERMAX; ++h) {
+                    const int d = per * call + h;
+                    if (h < per && d < ndim) {
+                        double x;
+                        if (!FAST && replay) x = a.u_replay[li * ndim + d];
+                        else if (w32) x = u32(rw[h]);
+                        else x = u52(rw[(2 * h) & 3], rw[(2 * h + 1) & 3]);
+                        // native draws lie strictly inside (0,1); replayed ones get the full check
+                        if constexpr (fused) {
+                            if constexpr (FAST) pdf_acc_dim<KIND, 0>(dens, pa, d, x);
+                            else pdf_acc_dim<KIND, 2>(dens, pa, d, x);
+                        }
+                        if constexpr (OUT) {
+                            // (N, ndim) row-major, integration.py:45.  Compile-time ndim: the row is staged in
+                            // registers and leaves as 256- / 128-bit stores (one contiguous 8 ndim byte run per
+                            // thread); scalar stores of a 128-byte-strided row reach a third of the bandwidth.
+                            if constexpr (NDIM_T != 0) xrow[d] = x;
+                            else if (a.x_out) a.x_out[li * ndim + d] = x;
+                        }
                     }
                 }
             }
@@ -373,6 +367,11 @@ __global__ void __launch_bounds__(256) plain_sample_kernel(const __grid_constant
     }
 }
 
+}  // namespace hepmc
+
+#include "vegas_fast.cuh"
+
+namespace hepmc {
 
 // fast-path launchers, one translation unit per density kind (integrate_fast_*.cu)
 // `out`: per-point outputs (x, f, w, idx) requested -> the OUT instance of the same kernel
@@ -395,16 +394,32 @@ int launch_fast_none(bool vegas, bool out, int, const Dens&, const SampleArgs&, 
         }                                                                                                   \
         return 0;                                                                                           \
     }
+#define HEPMC_VFAST_GO(KIND, ND, OUT, RNG, KP)                                                              \
+    do {                                                                                                    \
+        HEPMC_CUDA(cudaFuncSetAttribute(vegas_fast_kernel<KIND, ND, RNG, OUT, KP>,                          \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        HEPMC_CUDA(cudaFuncSetAttribute(vegas_fast_kernel<KIND, ND, RNG, OUT, KP>,                          \
+                                        cudaFuncAttributePreferredSharedMemoryCarveout, 100));              \
+        vegas_fast_kernel<KIND, ND, RNG, OUT, KP><<<blocks, 256, smem, st>>>(dens, a);                      \
+    } while (0)
+#define HEPMC_VFAST_KP(KIND, ND, OUT, RNG)                                                                  \
+    do {                                                                                                    \
+        if (a.K <= 16) HEPMC_VFAST_GO(KIND, ND, OUT, RNG, 16);                                              \
+        else HEPMC_VFAST_GO(KIND, ND, OUT, RNG, 0);                                                         \
+    } while (0)
 #define HEPMC_FAST_LAUNCH(KIND, ND, OUT)                                                                    \
     do {                                                                                                    \
         if (vegas) {                                                                                        \
-            HEPMC_CUDA(cudaFuncSetAttribute(vegas_sample_kernel<KIND, ND, true, OUT>,                       \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-            HEPMC_CUDA(cudaFuncSetAttribute(vegas_sample_kernel<KIND, ND, true, OUT>,                       \
-                                            cudaFuncAttributePreferredSharedMemoryCarveout, 100));          \
-            vegas_sample_kernel<KIND, ND, true, OUT><<<blocks, threads, smem, st>>>(dens, a);               \
+            if (a.rng_mode == HEPMC_RNG_U32_R7) HEPMC_VFAST_KP(KIND, ND, OUT, HEPMC_RNG_U32_R7);            \
+            else if (a.rng_mode == HEPMC_RNG_U32_R10) HEPMC_VFAST_KP(KIND, ND, OUT, HEPMC_RNG_U32_R10);     \
+            else HEPMC_VFAST_KP(KIND, ND, OUT, HEPMC_RNG_U52_R10);                                          \
         } else {                                                                                            \
-            plain_sample_kernel<KIND, ND, true, OUT><<<blocks, 256, 0, st>>>(dens, a);                      \
+            if (a.rng_mode == HEPMC_RNG_U32_R7)                                                             \
+                plain_sample_kernel<KIND, ND, true, OUT, HEPMC_RNG_U32_R7><<<blocks, 256, 0, st>>>(dens, a); \
+            else if (a.rng_mode == HEPMC_RNG_U32_R10)                                                       \
+                plain_sample_kernel<KIND, ND, true, OUT, HEPMC_RNG_U32_R10><<<blocks, 256, 0, st>>>(dens, a); \
+            else                                                                                            \
+                plain_sample_kernel<KIND, ND, true, OUT, HEPMC_RNG_U52_R10><<<blocks, 256, 0, st>>>(dens, a); \
         }                                                                                                   \
     } while (0)
 #define HEPMC_FAST_CASE(KIND, ND)                                                                           \

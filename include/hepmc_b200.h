@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HEPMC_B200_ABI_VERSION 1
+#define HEPMC_B200_ABI_VERSION 2
 #define HEPMC_MAX_DIM 32          /* max dimensionality of a built-in density      */
 #define HEPMC_MAX_DIVISIONS 255   /* max VEGAS bins per axis (bin ids are bytes)    */
 #define HEPMC_N_SLOTS 8           /* fixed reduction slots: GPU-count invariance    */
@@ -89,6 +89,21 @@ int hepmc_device_info(int device, int64_t* out5);
  * returns the elapsed milliseconds (CUDA events, synchronises) and the flop count. */
 int hepmc_fp64_probe(int64_t iters, double* ms_out, double* flops_out, void* stream);
 
+/* ---- native generator --------------------------------------------------------------
+ * The integrators' native draws (the counterpart of np.random.randint / np.random.rand in
+ * stratified_volume.py:110-121 and np.random.random in integration.py:41) come in three
+ * modes, chosen per call (`rng_mode`):
+ *   HEPMC_RNG_U52_R10 (default): 52-bit uniforms / 64 random bits per (bin, offset) pair,
+ *                                Philox4x32-10, two axes per Philox call;
+ *   HEPMC_RNG_U32_R10:           32 random bits per axis: uniform (w + 1/2) 2^-32; VEGAS
+ *                                t = K w: bin = t >> 32, offset = (t mod 2^32 + 1/2) 2^-32
+ *                                (bin probabilities within 2^-32 of 1/K); four axes per call;
+ *   HEPMC_RNG_U32_R7:            the same with Philox4x32-7 (the smallest round count that
+ *                                passes BigCrush in Salmon et al., SC'11; Random123 KATs).
+ * Counters are the same in every mode (item index, call index, stream id), so results stay
+ * independent of the GPU count.  RAMBO and the chain kernels always use 52-bit uniforms. */
+enum hepmc_rng_mode { HEPMC_RNG_U52_R10 = 0, HEPMC_RNG_U32_R10 = 1, HEPMC_RNG_U32_R7 = 2, HEPMC_RNG_MODES = 3 };
+
 /* ---- densities: replaces Density.pdf/pot/pot_gradient/pdf_gradient ---------------- */
 /* xs_dev: (n, ndim) row-major.  out_dev: (n,) or (n, ndim).
  * Replaces camel.py:20-45,87-100; banana.py:13-51; gaussian.py:30-47; uniform.py:15-31;
@@ -113,7 +128,7 @@ int64_t hepmc_default_chunk(int64_t n_total);
  * are written, so first_index may then be any global index (point i always uses counter
  * first_index + i). */
 int hepmc_plain_mc_sample(const hepmc_density_t* dens, int64_t n, int64_t first_index, int64_t chunk,
-                          uint64_t seed, uint32_t stream_id, const double* u_replay_dev,
+                          uint64_t seed, uint32_t stream_id, int rng_mode, const double* u_replay_dev,
                           double* data_dev, double* f_dev, double* partials_dev, void* stream);
 
 /* Generic ordered reduction of (count, mean, M2) rows: rows [row_begin[s], row_begin[s+1])
@@ -140,7 +155,7 @@ int hepmc_stats_partials(const double* values_dev, const double* weights_dev, do
  * Partials: stats_partials_dev (n_chunks,3) and hist_partials_dev (n_chunks, ndim*K),
  * hist[d*K+k] = sum of f*w over the chunk's points with bin k on axis d. */
 int hepmc_vegas_sample(const hepmc_density_t* dens, const double* grid_dev, int ndim, int divisions,
-                       int64_t n, int64_t first_index, int64_t chunk, uint64_t seed, uint32_t stream_id,
+                       int64_t n, int64_t first_index, int64_t chunk, uint64_t seed, uint32_t stream_id, int rng_mode,
                        const int64_t* idx_replay_dev, const double* u_replay_dev,
                        double* x_dev, double* f_dev, double* w_dev, int64_t* idx_dev,
                        double* stats_partials_dev, double* hist_partials_dev, void* stream);
@@ -169,7 +184,7 @@ int64_t hepmc_vegas_workspace_bytes(int ndim, int divisions, int64_t n);
  * reduce, grid update) enqueued back to back, no host synchronisation.  est_var_dev
  * (iterations, 2).  Iteration j uses stream id stream_id0 + j. */
 int hepmc_vegas_integrate(const hepmc_density_t* dens, double* grid_dev, int ndim, int divisions,
-                          int64_t n, int iterations, double c, uint64_t seed, uint32_t stream_id0,
+                          int64_t n, int iterations, double c, uint64_t seed, uint32_t stream_id0, int rng_mode,
                           double* est_var_dev, void* workspace_dev, int64_t workspace_bytes,
                           void* stream);
 

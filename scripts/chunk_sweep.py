@@ -20,7 +20,7 @@ for n in (10**9, 10**9 // 8):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             _lib.call("hepmc_vegas_sample", ctypes.byref(blk), _lib.ptr(grid), NDIM, K, n, 0, chunk, 1234, 100 + i,
-                      None, None, None, None, None, None, _lib.ptr(sp), _lib.ptr(hp), _lib.stream_ptr())
+                      H.rng.mode_code(), None, None, None, None, None, None, _lib.ptr(sp), _lib.ptr(hp), _lib.stream_ptr())
             b.record(); torch.cuda.synchronize()
             if i >= 2: ts.append(a.elapsed_time(b))
         print("n %.3g chunk %6d: %4d CTAs = %6.2f waves  %.3f ms  %.3e points/s" % (n, chunk, nc, nc / 444, np.mean(ts), n / np.mean(ts) * 1e3))

@@ -1,0 +1,88 @@
+// Development harness: times vegas_fast_kernel<CAMEL,16,...> alone (CUDA events) for the three RNG
+// modes at 1e9 points, uniform 16x15 grid, and prints a checksum of the partial rows so that build
+// variants (-D flags) can be compared for speed and for identical results.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false --expt-relaxed-constexpr
+//        -I hepmc_b200/csrc [-D...] scripts/vegas_kernel_bench.cu -o scripts/_build/vkb_<tag>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include "integrate_kernels.cuh"
+
+namespace hepmc {
+void set_error(const char*, ...) {}
+int check_cuda(cudaError_t e, const char* w) { if (e != cudaSuccess) { printf("CUDA error %s at %s\n", cudaGetErrorString(e), w); exit(1); } return 0; }
+}
+using namespace hepmc;
+
+#ifndef BENCH_NDIM
+#define BENCH_NDIM 16
+#endif
+#ifndef BENCH_CHUNK
+#define BENCH_CHUNK 32768
+#endif
+
+template <int RNG>
+static void run(const char* tag, const Dens& dens, SampleArgs a, int blocks, size_t smem, int reps) {
+    auto kern = vegas_fast_kernel<HEPMC_CAMEL, BENCH_NDIM, RNG, false, 16>;
+    check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr");
+    check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100), "attr2");
+    a.rng_mode = RNG;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f, sum = 0.f;
+    for (int i = 0; i < reps + 2; ++i) {
+        a.stream_id = 100 + i;
+        cudaEventRecord(e0);
+        kern<<<blocks, 256, smem>>>(dens, a);
+        cudaEventRecord(e1);
+        check_cuda(cudaEventSynchronize(e1), "sync");
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (i >= 2) { best = fminf(best, ms); sum += ms; }
+    }
+    // checksum of the last launch
+    std::vector<double> st(3 * (size_t)blocks), hi((size_t)blocks * BENCH_NDIM * a.K);
+    cudaMemcpy(st.data(), a.stats_partials, st.size() * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hi.data(), a.hist_partials, hi.size() * 8, cudaMemcpyDeviceToHost);
+    double cs = 0, ch = 0, cn = 0;
+    for (int b = 0; b < blocks; ++b) { cn += st[3 * b]; cs += st[3 * b + 1] * st[3 * b]; }
+    for (double v : hi) ch += v;
+    int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, smem);
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
+    printf("%-8s mean %.3f ms best %.3f ms  %.4g pts/s  regs %d blocks/SM %d  n %.0f sum_wf %.17g sum_hist %.17g\n", tag, sum / reps, best,
+           (double)a.n / (sum / reps * 1e-3), fa.numRegs, nb, cn, cs, ch);
+}
+
+int main(int argc, char** argv) {
+    const int64_t n = argc > 1 ? (int64_t)atof(argv[1]) : 1000000000LL;
+    const int K = 15, ndim = BENCH_NDIM;
+    Dens dens{};
+    dens.kind = HEPMC_CAMEL; dens.ndim = ndim;
+    const double cov = 0.005;
+    for (int d = 0; d < ndim; ++d) { dens.a[d] = 1.0 / 3; dens.b[d] = 2.0 / 3; }
+    dens.s0 = sqrt(1.0 / cov); dens.s1 = ndim * log(2 * M_PI) + ndim * log(cov); dens.s2 = cov;
+    std::vector<double> grid((size_t)ndim * (2 * K + 1));
+    for (int d = 0; d < ndim; ++d) {
+        // mildly non-uniform deterministic grid
+        double tot = 0; std::vector<double> sz(K);
+        for (int k = 0; k < K; ++k) { sz[k] = 1.0 + 0.5 * sin(0.7 * k + d); tot += sz[k]; }
+        double cum = 0; grid[d * (2 * K + 1)] = 0;
+        for (int k = 0; k < K; ++k) { sz[k] /= tot; cum += sz[k]; grid[d * (2 * K + 1) + k + 1] = cum; grid[d * (2 * K + 1) + K + 1 + k] = sz[k]; }
+    }
+    double* g_dev; cudaMalloc(&g_dev, grid.size() * 8); cudaMemcpy(g_dev, grid.data(), grid.size() * 8, cudaMemcpyHostToDevice);
+    const int64_t chunk = BENCH_CHUNK;
+    const int blocks = (int)((n + chunk - 1) / chunk);
+    SampleArgs a{};
+    a.grid = g_dev; a.ndim = ndim; a.K = K; a.n = n; a.first_index = 0; a.chunk = chunk; a.seed = 1234;
+    a.kpow = pow((double)K, (double)ndim);
+    a.keys = philox_expand(a.seed);
+    set_camel_centre(a, dens);
+    cudaMalloc(&a.stats_partials, (size_t)blocks * 3 * 8);
+    cudaMalloc(&a.hist_partials, (size_t)blocks * ndim * K * 8);
+    const size_t smem = vegas_fast_smem_bytes(ndim, K, 256);
+    printf("n %lld chunk %lld blocks %d smem %zu\n", (long long)n, (long long)chunk, blocks, smem);
+    run<0>("u52r10", dens, a, blocks, smem, 4);
+    run<1>("u32r10", dens, a, blocks, smem, 4);
+    run<2>("u32r7", dens, a, blocks, smem, 4);
+    return 0;
+}

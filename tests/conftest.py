@@ -40,3 +40,14 @@ def assert_close(a, b, rtol=1e-12, atol=0.0, msg=""):
         i = np.argmax(err - tol)
         raise AssertionError("%s: %d/%d outside rtol=%g; worst |%r - %r| = %g" % (
             msg, bad.sum(), bad.size, rtol, a[fin][i], b[fin][i], err[i]))
+
+
+@pytest.fixture(autouse=True)
+def _default_rng_mode():
+    """Every test starts in the product's default draw mode (tests that switch modes need no clean-up)."""
+    try:
+        import hepmc_b200 as H
+        H.rng.set_mode(H.rng.DEFAULT_MODE)
+    except Exception:
+        pass
+    yield

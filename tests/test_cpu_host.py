@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), "missing symbol " + name
     assert set(names) == set(_lib.SIGNATURES), "ctypes table and header disagree"
-    assert _lib.load().hepmc_abi_version() == 1
+    assert _lib.load().hepmc_abi_version() == 2
 
 
 def test_struct_layout_matches_header():

@@ -95,12 +95,15 @@ def test_plain_mc_replay(ndim):
     assert np.array_equal(s.data, g["data_%d" % ndim])
 
 
-def test_plain_mc_native_matches_oracle_draws():
+@pytest.mark.parametrize("mode", ["u32r10", "u52r10", "u32r7"])
+@pytest.mark.parametrize("ndim", [3, 16, 20])
+def test_plain_mc_native_matches_oracle_draws(mode, ndim):
+    H.rng.set_mode(mode)
     H.seed(99)
-    n, ndim = 5000, 3
+    n = 5000
     s = H.PlainMC(ndim)(H.densities.Camel(ndim), n)
-    u = O.philox_uniforms(99, 0, np.arange(n), ndim)
-    assert np.array_equal(s.data, u)                      # bit-exact Philox + u52
+    u = O.philox_uniforms(99, 0, np.arange(n), ndim, mode)
+    assert np.array_equal(s.data, u)                      # bit-exact Philox + bits -> double
     integral, err, f = O.plain_mc(O.camel_pdf, u)
     assert_close(s.function_values, f, RTOL)
     assert_close(s.integral, integral, RTOL)
@@ -150,13 +153,18 @@ def test_vegas_grid_trajectory_replay():
         assert_close(np.stack(mc.volumes.bounds), ref[k], RTOL, atol=1e-15, msg="bounds after %d" % k)
 
 
-@pytest.mark.parametrize("ndim,K,n", [(2, 50, 5000), (16, 15, 3000), (5, 7, 2500), (1, 4, 300)])
-def test_vegas_native_matches_oracle_draws(ndim, K, n):
+@pytest.mark.parametrize("mode", ["u32r10", "u52r10", "u32r7"])
+@pytest.mark.parametrize("ndim,K,n", [(2, 50, 5000), (16, 15, 3000), (5, 7, 2500), (1, 4, 300), (9, 16, 2100), (3, 17, 700),
+                                      (20, 6, 1500)])
+def test_vegas_native_matches_oracle_draws(ndim, K, n, mode):
+    """Every RNG mode, throughput instances (ndim <= 16; K <= 16 and K > 16 layouts) and the generic
+    kernel (ndim = 20), draw for draw against the oracle."""
+    H.rng.set_mode(mode)
     H.seed(4321)
     iters = 3
     mc = H.VegasMC(ndim, divisions=K)
     s = mc(H.densities.Camel(ndim), n, iters, chi=True)
-    tapes = [O.philox_vegas_draws(4321, j, np.arange(n), ndim, K) for j in range(iters)]
+    tapes = [O.philox_vegas_draws(4321, j, np.arange(n), ndim, K, mode) for j in range(iters)]
     idx = np.stack([t[0] for t in tapes])
     u = np.stack([t[1] for t in tapes])
     r = O.vegas(O.camel_pdf, ndim, K, idx, u, chi=True)
@@ -177,8 +185,22 @@ def test_vegas_two_kernel_path_equals_fused():
     b = H.VegasMC(3, divisions=9)
     dens = H.densities.Camel(3)
     sb = b(lambda x, y, z: dens.pdf(torch.stack((x, y, z), dim=1)), 4000, 3)
-    assert sa.integral == sb.integral and sa.integral_err == sb.integral_err
-    assert np.array_equal(np.stack(a.volumes.bounds), np.stack(b.volumes.bounds))
+    # same draws, same weights, same reduction order; the fused kernel evaluates the camel in centred form
+    # (vegas_fast.cuh), the density kernel in the reference's form: values agree to a few ulp
+    assert np.array_equal(sa.data, sb.data) and np.array_equal(sa.weights, sb.weights)
+    assert_close(sa.function_values, sb.function_values, 1e-13, atol=1e-300)
+    assert_close(sa.integral, sb.integral, 1e-13)
+    assert_close(sa.integral_err, sb.integral_err, 1e-12)
+    assert_close(np.stack(a.volumes.bounds), np.stack(b.volumes.bounds), 1e-12)
+    # a user integrand on both paths' inputs: the fused-histogram and two-kernel reductions are bit-identical
+    H.seed(5)
+    c = H.VegasMC(3, divisions=9)
+    sc = c(H.densities.Uniform(3), 4000, 3)
+    H.seed(5)
+    d = H.VegasMC(3, divisions=9)
+    sd = d(lambda x, y, z: torch.ones_like(x), 4000, 3)
+    assert sc.integral == sd.integral and sc.integral_err == sd.integral_err
+    assert np.array_equal(np.stack(c.volumes.bounds), np.stack(d.volumes.bounds))
 
 
 def test_vegas_statistics_and_determinism():
@@ -215,7 +237,8 @@ def test_vegas_gpu_count_invariance_at_abi_level():
             hp = torch.zeros((max(ncl, 1), ndim * K), dtype=torch.float64, device=dev)
             if n_local:
                 _lib.call("hepmc_vegas_sample", ctypes.byref(blk), _lib.ptr(grid), ndim, K, n_local, first, chunk,
-                          77, 0, None, None, None, None, None, None, _lib.ptr(sp), _lib.ptr(hp), _lib.stream_ptr())
+                          77, 0, H.rng.mode_code(), None, None, None, None, None, None, _lib.ptr(sp), _lib.ptr(hp),
+                          _lib.stream_ptr())
             ss = torch.zeros((len(begins) - 1, 3), dtype=torch.float64, device=dev)
             sh = torch.zeros((len(begins) - 1, ndim * K), dtype=torch.float64, device=dev)
             _lib.call("hepmc_reduce_stats", _lib.ptr(sp), _lib.i64_array(begins), len(begins) - 1, _lib.ptr(ss), _lib.stream_ptr())
@@ -872,7 +895,7 @@ def test_edge_cases_empty_and_ragged():
     for n in (1, 31, 255, 257, 2047, 2049, 4097):
         H.seed(50 + n)
         s = H.PlainMC(3)(H.densities.Camel(3), n)
-        u = O.philox_uniforms(50 + n, 0, np.arange(n), 3)
+        u = O.philox_uniforms(50 + n, 0, np.arange(n), 3, H.rng.get_mode())
         integral, err, f = O.plain_mc(O.camel_pdf, u)
         assert np.array_equal(s.data, u)
         assert_close(s.integral, integral, RTOL)

@@ -221,6 +221,45 @@ def test_philox_kat():
         assert tuple(int(o[0]) for o in out) == exp
 
 
+def test_philox7_kat():
+    """Random123 known-answer vectors for Philox4x32-7 (kat_vectors: philox4x32 7 ...)."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a))]
+    for ctr, key, exp in kat:
+        out = O.philox4x32(*[np.array([c], dtype=np.uint64) for c in ctr], key[0], key[1], rounds=7)
+        assert tuple(int(o[0]) for o in out) == exp
+
+
+def test_32bit_draw_conventions():
+    """u32 / vegas_bin_frac32: exact values, the kernels' exponent trick, the joint (bin, offset) law."""
+    w = np.array([0, 1, 0x80000000, 0xffffffff, 0x12345678], dtype=np.uint32)
+    u = O.u32(w)
+    assert u[0] == 2.0 ** -33 and u[3] == 1.0 - 2.0 ** -33 and np.all((u > 0) & (u < 1))
+    # as_double(0x41300000 : w) - (2^20 - 2^-33), csrc/integrate_kernels.cuh u32()
+    trick = ((np.uint64(0x41300000) << np.uint64(32)) | w.astype(np.uint64)).view(np.float64) - (2.0 ** 20 - 2.0 ** -33)
+    assert np.array_equal(trick, u)
+    for k in (1, 2, 15, 50, 255):
+        rs = np.random.RandomState(k)
+        ww = np.concatenate([w, rs.randint(0, 2 ** 32, 20000, dtype=np.uint64).astype(np.uint32)])
+        b, f = O.vegas_bin_frac32(ww, k)
+        assert b.min() >= 0 and b.max() < k and np.all((f > 0) & (f < 1))
+        # (bin + offset) / K reproduces the uniform the word stands for, shifted by half a quantum of the offset
+        t = (b + f) / k
+        assert np.allclose(t, (ww.astype(np.float64) + 0.5 / k) * 2.0 ** -32, rtol=0, atol=2e-16)
+    # all three modes of the draw helpers agree on shapes and differ in values
+    idx = np.arange(50)
+    d52 = O.philox_vegas_draws(7, 0, idx, 5, 9, "u52r10")
+    d32 = O.philox_vegas_draws(7, 0, idx, 5, 9, "u32r10")
+    d7 = O.philox_vegas_draws(7, 0, idx, 5, 9, "u32r7")
+    assert d52[0].shape == d32[0].shape == d7[0].shape == (5, 50)
+    assert not np.array_equal(d52[1], d32[1]) and not np.array_equal(d32[1], d7[1])
+    u = O.philox_uniforms(7, 0, idx, 6, "u32r10")
+    w4 = O.philox_words(7, 0, idx, 2)
+    assert np.array_equal(u[:, 5], O.u32(w4[:, 1, 1]))
+
+
 def test_uniform_conventions():
     a = np.array([0, 0xffffffff, 0x12345678], dtype=np.uint32)
     b = np.array([0, 0xffffffff, 0x9abcdef0], dtype=np.uint32)
