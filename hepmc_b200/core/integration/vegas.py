@@ -3,9 +3,9 @@
 Per iteration j:  uniform bin + offset per axis -> point, weight w = prod(sizes) * K^ndim,
 wf = f * w;  est_j = mean(wf), var_j = var0(wf)/N;  per-(axis, bin) first moments drive
 the damped grid update  inv = K*est[d,k] * c/(j+1+c) + (est_j/size) * (j+1)/(j+1+c).
-The whole iteration is three launches (fused sample kernel, ordered slot reduction, grid
-update) with no host synchronisation; under torch.distributed one all-gather of the
-8 slot partials ((3 + ndim*K) doubles each) is the only exchange.
+The whole iteration is four launches (fused sample kernel, two-level ordered slot reduction into
+packed slot rows, grid update) with no host synchronisation; under torch.distributed one
+all-gather of the 8 packed slot rows ((3 + ndim*K) doubles each) is the only exchange.
 """
 import ctypes
 import math
@@ -103,9 +103,12 @@ class VegasMC(object):
         cols = ndim * K
         stats_p = torch.zeros((max(nc_local, 1), 3), dtype=torch.float64, device=dev)
         hist_p = torch.zeros((max(nc_local, 1), cols), dtype=torch.float64, device=dev)
+        # packed slot rows [count, mean, M2, hist...]: written by the fused slot reduction, all-gathered as
+        # they are, read in place by the grid update (no slicing or copying between the three)
         slot_local = torch.zeros((n_slots_local, 3 + cols), dtype=torch.float64, device=dev)
-        slot_stats_l = torch.zeros((n_slots_local, 3), dtype=torch.float64, device=dev)
-        slot_hist_l = torch.zeros((n_slots_local, cols), dtype=torch.float64, device=dev)
+        slots_all = slot_local if ws == 1 else torch.empty((_lib.N_SLOTS, 3 + cols), dtype=torch.float64, device=dev)
+        scratch = torch.empty(int(_lib.load().hepmc_reduce_slots_scratch_bytes(n_slots_local, cols)) // 8 + 1,
+                              dtype=torch.float64, device=dev)
         begins_c = _lib.i64_array(begins)
         seed = rng.get_seed()
         sid0 = rng.next_stream(iterations)
@@ -140,17 +143,11 @@ class VegasMC(object):
                     f = engine.call_integrand(fn, [x[d] for d in range(ndim)])
                     _lib.call("hepmc_vegas_accumulate", _lib.ptr(f), _lib.ptr(w), _lib.ptr(idx), ndim, K,
                               n_local, chunk, _lib.ptr(stats_p), _lib.ptr(hist_p), st)
-            _lib.call("hepmc_reduce_stats", _lib.ptr(stats_p), begins_c, n_slots_local, _lib.ptr(slot_stats_l), st)
-            _lib.call("hepmc_reduce_hist", _lib.ptr(hist_p), begins_c, n_slots_local, cols, _lib.ptr(slot_hist_l), st)
+            _lib.call("hepmc_reduce_slots", _lib.ptr(stats_p), _lib.ptr(hist_p), begins_c, n_slots_local, cols,
+                      _lib.ptr(slot_local), _lib.ptr(scratch), st)
             if ws > 1:
-                slot_local[:, :3] = slot_stats_l
-                slot_local[:, 3:] = slot_hist_l
-                slots = parallel.gather_slots(slot_local)
-                slot_stats = slots[:, :3].contiguous()
-                slot_hist = slots[:, 3:].contiguous()
-            else:
-                slot_stats, slot_hist = slot_stats_l, slot_hist_l
-            _lib.call("hepmc_vegas_update_grid", _lib.ptr(slot_stats), _lib.ptr(slot_hist), slot_stats.shape[0],
+                parallel.gather_slots(slot_local, out=slots_all)
+            _lib.call("hepmc_vegas_update_grid_packed", _lib.ptr(slots_all), slots_all.shape[0],
                       _lib.ptr(grid), ndim, K, float(self.c), j, _lib.ptr(est_var), st)
             if kept is not None and not fused and n_local:
                 kept["function_values"][j * n_local:(j + 1) * n_local] = f

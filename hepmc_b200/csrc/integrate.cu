@@ -99,35 +99,28 @@ struct RowRanges {
     int n_out;
 };
 
-// one warp per output slot: lane l merges a contiguous sub-range in row order, then the
-// 32 lane results are merged in lane order.  The tree depends on the range only.
-__global__ void __launch_bounds__(32) reduce_stats_kernel(const double* __restrict__ rows,
-                                                          const __grid_constant__ RowRanges rr,
-                                                          double* __restrict__ out) {
-    const int s = blockIdx.x, lane = threadIdx.x;
+// one CTA per output slot: thread t merges the rows b + t, b + t + 256, ... in row order, then the 256
+// thread results are merged in a fixed tree (warp butterfly, lower lane on the left; the 8 warp
+// results in warp order).  The tree depends on the slot's row range only, never on the GPU count.
+// (Round 1 used ONE warp per slot: 119 dependent merges per lane plus a 32-step serial lane merge,
+// 80 us per iteration -- the largest fixed cost of the 8-GPU step.)
+__global__ void __launch_bounds__(256) reduce_stats_kernel(const double* __restrict__ rows,
+                                                           const __grid_constant__ RowRanges rr,
+                                                           double* __restrict__ out, int out_stride) {
+    __shared__ Stats s_w[8];
+    const int s = blockIdx.x;
     const int64_t b = rr.begin[s], e = rr.begin[s + 1];
-    const int64_t len = e - b;
-    const int64_t per = (len + 31) / 32;
-    int64_t r0 = b + lane * per, r1 = r0 + per;
-    if (r0 > e) r0 = e;
-    if (r1 > e) r1 = e;
     Stats acc{0.0, 0.0, 0.0};
-    for (int64_t r = r0; r < r1; ++r) {
+    for (int64_t r = b + threadIdx.x; r < e; r += 256) {
         Stats t{rows[r * 3], rows[r * 3 + 1], rows[r * 3 + 2]};
         acc = merge(acc, t);
     }
-    Stats total{0.0, 0.0, 0.0};
-    for (int l = 0; l < 32; ++l) {
-        Stats t;
-        t.n = __shfl_sync(0xffffffffu, acc.n, l);
-        t.mean = __shfl_sync(0xffffffffu, acc.mean, l);
-        t.m2 = __shfl_sync(0xffffffffu, acc.m2, l);
-        total = merge(total, t);
-    }
-    if (lane == 0) {
-        out[s * 3] = total.n;
-        out[s * 3 + 1] = total.mean;
-        out[s * 3 + 2] = total.m2;
+    const Stats total = block_merge<256>(acc, s_w);
+    if (threadIdx.x == 0) {
+        double* o = out + (size_t)s * out_stride;
+        o[0] = total.n;
+        o[1] = total.mean;
+        o[2] = total.m2;
     }
 }
 
@@ -162,18 +155,90 @@ __global__ void __launch_bounds__(kHistLanes * kHistCols) reduce_hist_kernel(con
     if (ry == 0 && col < ncols) out[(size_t)s * ncols + col] = part[0][cx];
 }
 
+// ------------------------------------------------------------------ fused slot reduction (VEGAS iteration)
+// Chunk partial rows (count, mean, M2 | hist[cols]) of every slot -> one PACKED row per slot
+// [count, mean, M2, hist...] (the all-gather send buffer), in two levels so that one slot's rows (3815
+// at 1e9 points) are read by kSlotGroups * (column tiles + 1) CTAs instead of 8:
+//   level 1: group g of slot s owns the rows [b + len*g/G, b + len*(g+1)/G); histogram CTAs add them per
+//            column with 8 row lanes (rows r0+y, r0+y+8, ... in order, lanes combined in a fixed tree);
+//            the statistics CTA Chan-merges the group's rows (thread order, fixed tree);
+//   level 2: the G group partials of a slot are combined in group order.
+// Every order is a function of the slot's row range only: bit-identical at any GPU count.
+constexpr int kSlotGroups = 32;
+constexpr int kRedCols = 32, kRedLanes = 8;
+
+__global__ void __launch_bounds__(kRedCols * kRedLanes) reduce_slots_l1_kernel(
+    const double* __restrict__ stats_rows, const double* __restrict__ hist_rows, const __grid_constant__ RowRanges rr,
+    int ncols, double* __restrict__ scratch /* (n_out, G, 3 + ncols) */) {
+    __shared__ double part[kRedLanes][kRedCols];
+    __shared__ Stats s_w[8];
+    const int s = blockIdx.z, g = blockIdx.y;
+    const int64_t b = rr.begin[s], len = rr.begin[s + 1] - b;
+    const int64_t r0 = b + len * g / kSlotGroups, r1 = b + len * (g + 1) / kSlotGroups;
+    double* out = scratch + ((size_t)s * kSlotGroups + g) * (3 + ncols);
+    const int ntile = (ncols + kRedCols - 1) / kRedCols;
+    if ((int)blockIdx.x == ntile) {   // statistics of the group
+        Stats acc{0.0, 0.0, 0.0};
+        for (int64_t r = r0 + threadIdx.x; r < r1; r += kRedCols * kRedLanes) {
+            Stats t{stats_rows[r * 3], stats_rows[r * 3 + 1], stats_rows[r * 3 + 2]};
+            acc = merge(acc, t);
+        }
+        const Stats total = block_merge<kRedCols * kRedLanes>(acc, s_w);
+        if (threadIdx.x == 0) { out[0] = total.n; out[1] = total.mean; out[2] = total.m2; }
+        return;
+    }
+    const int cx = threadIdx.x % kRedCols, ry = threadIdx.x / kRedCols;
+    const int col = blockIdx.x * kRedCols + cx;
+    double acc = 0.0;
+    if (col < ncols)
+        for (int64_t r = r0 + ry; r < r1; r += kRedLanes) acc += hist_rows[r * ncols + col];
+    part[ry][cx] = acc;
+    __syncthreads();
+#pragma unroll
+    for (int half = kRedLanes / 2; half > 0; half >>= 1) {
+        if (ry < half) part[ry][cx] += part[ry + half][cx];
+        __syncthreads();
+    }
+    if (ry == 0 && col < ncols) out[3 + col] = part[0][cx];
+}
+
+__global__ void __launch_bounds__(256) reduce_slots_l2_kernel(const double* __restrict__ scratch, int ncols,
+                                                              double* __restrict__ packed /* (n_out, 3 + ncols) */) {
+    const int s = blockIdx.x;
+    const int row = 3 + ncols;
+    const double* in = scratch + (size_t)s * kSlotGroups * row;
+    double* out = packed + (size_t)s * row;
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+        double acc = 0.0;
+#pragma unroll 8
+        for (int g = 0; g < kSlotGroups; ++g) acc += in[(size_t)g * row + 3 + c];
+        out[3 + c] = acc;
+    }
+    if (threadIdx.x == 0) {
+        Stats t{0.0, 0.0, 0.0};
+        for (int g = 0; g < kSlotGroups; ++g) {
+            Stats u{in[(size_t)g * row], in[(size_t)g * row + 1], in[(size_t)g * row + 2]};
+            t = merge(t, u);
+        }
+        out[0] = t.n; out[1] = t.mean; out[2] = t.m2;
+    }
+}
+
 // ------------------------------------------------------------------ grid adaptation (one CTA)
-__global__ void __launch_bounds__(256) vegas_update_kernel(const double* __restrict__ slot_stats,
-                                                           const double* __restrict__ slot_hist, int n_slots,
-                                                           double* __restrict__ grid, int ndim, int K, double c,
-                                                           int j, double* __restrict__ est_var) {
+// slot s: statistics at slot_stats + s*stride, histogram at slot_hist + s*stride (stride 3 / ndim*K for
+// separate arrays; 3 + ndim*K for the packed rows of the all-gather buffer)
+__global__ void __launch_bounds__(256) vegas_update_kernel(const double* __restrict__ slot_stats, int64_t stats_stride,
+                                                           const double* __restrict__ slot_hist, int64_t hist_stride,
+                                                           int n_slots, double* __restrict__ grid, int ndim, int K,
+                                                           double c, int j, double* __restrict__ est_var) {
     extern __shared__ double sm[];
     double* s_new = sm;  // ndim*K new sizes
     __shared__ double s_est, s_n;
     if (threadIdx.x == 0) {
         Stats t{0.0, 0.0, 0.0};
         for (int s = 0; s < n_slots; ++s) {
-            Stats u{slot_stats[s * 3], slot_stats[s * 3 + 1], slot_stats[s * 3 + 2]};
+            const double* ss = slot_stats + (size_t)s * stats_stride;
+            Stats u{ss[0], ss[1], ss[2]};
             t = merge(t, u);
         }
         s_est = t.mean;               // est_j = mean(weighted)           vegas.py:110
@@ -188,7 +253,7 @@ __global__ void __launch_bounds__(256) vegas_update_kernel(const double* __restr
     for (int q = threadIdx.x; q < ndim * K; q += blockDim.x) {
         const int d = q / K, k = q % K;
         double h = 0.0;
-        for (int s = 0; s < n_slots; ++s) h += slot_hist[(size_t)s * ndim * K + q];
+        for (int s = 0; s < n_slots; ++s) h += slot_hist[(size_t)s * hist_stride + q];
         const double estimate = h / n;                       // vegas.py:108-109
         const double size = grid[d * stride + K + 1 + k];
         const double old_v = est / size;                     // vegas.py:113
@@ -390,7 +455,7 @@ int hepmc_reduce_stats(const double* rows_dev, const int64_t* row_begin_host, in
     int e = fill_ranges(rr, row_begin_host, n_out, "hepmc_reduce_stats");
     if (e) return e;
     HEPMC_REQUIRE(rows_dev && out_dev, HEPMC_E_ARG, "hepmc_reduce_stats: NULL buffer");
-    reduce_stats_kernel<<<n_out, 32, 0, as_stream(stream)>>>(rows_dev, rr, out_dev);
+    reduce_stats_kernel<<<n_out, 256, 0, as_stream(stream)>>>(rows_dev, rr, out_dev, 3);
     HEPMC_LAUNCH_CHECK();
     return 0;
 }
@@ -482,7 +547,42 @@ int hepmc_vegas_update_grid(const double* slot_stats_dev, const double* slot_his
                   "hepmc_vegas_update_grid: bad sizes");
     const size_t smem = (size_t)ndim * divisions * 8;
     HEPMC_CUDA(cudaFuncSetAttribute(vegas_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vegas_update_kernel<<<1, 256, smem, as_stream(stream)>>>(slot_stats_dev, slot_hist_dev, n_slots, grid_dev, ndim,
+    vegas_update_kernel<<<1, 256, smem, as_stream(stream)>>>(slot_stats_dev, 3, slot_hist_dev, (int64_t)ndim * divisions,
+                                                             n_slots, grid_dev, ndim, divisions, c, j, est_var_dev);
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t hepmc_reduce_slots_scratch_bytes(int n_out, int ncols) {
+    return (int64_t)n_out * kSlotGroups * (3 + ncols) * 8;
+}
+
+int hepmc_reduce_slots(const double* stats_rows_dev, const double* hist_rows_dev, const int64_t* row_begin_host,
+                       int n_out, int ncols, double* packed_dev, void* scratch_dev, void* stream) {
+    RowRanges rr;
+    int e = fill_ranges(rr, row_begin_host, n_out, "hepmc_reduce_slots");
+    if (e) return e;
+    HEPMC_REQUIRE(stats_rows_dev && hist_rows_dev && packed_dev && scratch_dev && ncols >= 1, HEPMC_E_ARG,
+                  "hepmc_reduce_slots: bad arguments");
+    const int ntile = (ncols + kRedCols - 1) / kRedCols;
+    dim3 grid(ntile + 1, kSlotGroups, n_out);
+    reduce_slots_l1_kernel<<<grid, kRedCols * kRedLanes, 0, as_stream(stream)>>>(
+        stats_rows_dev, hist_rows_dev, rr, ncols, reinterpret_cast<double*>(scratch_dev));
+    reduce_slots_l2_kernel<<<n_out, 256, 0, as_stream(stream)>>>(reinterpret_cast<const double*>(scratch_dev), ncols,
+                                                                 packed_dev);
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+int hepmc_vegas_update_grid_packed(const double* packed_dev, int n_slots, double* grid_dev, int ndim, int divisions,
+                                   double c, int j, double* est_var_dev, void* stream) {
+    HEPMC_REQUIRE(packed_dev && grid_dev && est_var_dev, HEPMC_E_ARG, "hepmc_vegas_update_grid_packed: NULL buffer");
+    HEPMC_REQUIRE(n_slots >= 1 && ndim >= 1 && ndim <= HEPMC_MAX_DIM && divisions >= 1 && j >= 0, HEPMC_E_ARG,
+                  "hepmc_vegas_update_grid_packed: bad sizes");
+    const size_t smem = (size_t)ndim * divisions * 8;
+    const int64_t row = 3 + (int64_t)ndim * divisions;
+    HEPMC_CUDA(cudaFuncSetAttribute(vegas_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vegas_update_kernel<<<1, 256, smem, as_stream(stream)>>>(packed_dev, row, packed_dev + 3, row, n_slots, grid_dev, ndim,
                                                              divisions, c, j, est_var_dev);
     HEPMC_LAUNCH_CHECK();
     return 0;
@@ -496,7 +596,7 @@ int64_t hepmc_vegas_workspace_bytes(int ndim, int divisions, int64_t n) {
     const int64_t chunk = hepmc_default_chunk(n);
     const int64_t nc = (n + chunk - 1) / chunk;
     const int64_t cols = (int64_t)ndim * divisions;
-    return 8 * (nc * 3 + nc * cols + HEPMC_N_SLOTS * 3 + HEPMC_N_SLOTS * cols) + 256;
+    return 8 * (nc * 3 + nc * cols + HEPMC_N_SLOTS * (3 + cols)) + hepmc_reduce_slots_scratch_bytes(HEPMC_N_SLOTS, (int)cols) + 256;
 }
 
 int hepmc_vegas_integrate(const hepmc_density_t* dens, double* grid_dev, int ndim, int divisions,
@@ -514,20 +614,17 @@ int hepmc_vegas_integrate(const hepmc_density_t* dens, double* grid_dev, int ndi
     double* ws = reinterpret_cast<double*>(workspace_dev);
     double* stats_p = ws;
     double* hist_p = stats_p + nc * 3;
-    double* slot_stats = hist_p + nc * cols;
-    double* slot_hist = slot_stats + HEPMC_N_SLOTS * 3;
+    double* packed = hist_p + nc * cols;
+    double* scratch = packed + HEPMC_N_SLOTS * (3 + cols);
     int64_t begin[HEPMC_N_SLOTS + 1];
     slot_ranges(nc, begin);
     for (int j = 0; j < iterations; ++j) {
         int e = hepmc_vegas_sample(dens, grid_dev, ndim, divisions, n, 0, chunk, seed, stream_id0 + (uint32_t)j, rng_mode,
                                    nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats_p, hist_p, stream);
         if (e) return e;
-        e = hepmc_reduce_stats(stats_p, begin, HEPMC_N_SLOTS, slot_stats, stream);
+        e = hepmc_reduce_slots(stats_p, hist_p, begin, HEPMC_N_SLOTS, (int)cols, packed, scratch, stream);
         if (e) return e;
-        e = hepmc_reduce_hist(hist_p, begin, HEPMC_N_SLOTS, (int)cols, slot_hist, stream);
-        if (e) return e;
-        e = hepmc_vegas_update_grid(slot_stats, slot_hist, HEPMC_N_SLOTS, grid_dev, ndim, divisions, c, j,
-                                    est_var_dev, stream);
+        e = hepmc_vegas_update_grid_packed(packed, HEPMC_N_SLOTS, grid_dev, ndim, divisions, c, j, est_var_dev, stream);
         if (e) return e;
     }
     return 0;

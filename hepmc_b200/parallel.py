@@ -56,12 +56,13 @@ def item_span(n_total, rank=None, world_size=None):
     return first, last - first
 
 
-def gather_slots(local_rows):
-    """(n_local_slots, P) on every rank -> (N_SLOTS, P), slot order, on every rank."""
+def gather_slots(local_rows, out=None):
+    """(n_local_slots, P) on every rank -> (N_SLOTS, P), slot order, on every rank (into `out` if given)."""
     rank, ws = world()
     if ws == 1:
         return local_rows
-    out = torch.empty((N_SLOTS, local_rows.shape[1]), dtype=local_rows.dtype, device=local_rows.device)
+    if out is None:
+        out = torch.empty((N_SLOTS, local_rows.shape[1]), dtype=local_rows.dtype, device=local_rows.device)
     dist.all_gather_into_tensor(out, local_rows.contiguous())
     return out
 

@@ -178,6 +178,18 @@ int hepmc_vegas_update_grid(const double* slot_stats_dev, const double* slot_his
                             double* grid_dev, int ndim, int divisions, double c, int j,
                             double* est_var_dev, void* stream);
 
+/* The slot reduction of one VEGAS iteration in one call: chunk partial rows (stats (n_chunks,3), hist
+ * (n_chunks, ncols)) -> PACKED slot rows packed_dev (n_out, 3 + ncols) = [count, mean, M2, hist...], the
+ * layout that is all-gathered between GPUs (vegas.py:108-111).  Two levels with fixed row groups and a
+ * fixed combine order: bit-identical for any partition of the slots over GPUs.  scratch_dev:
+ * hepmc_reduce_slots_scratch_bytes(n_out, ncols) bytes of device memory. */
+int64_t hepmc_reduce_slots_scratch_bytes(int n_out, int ncols);
+int hepmc_reduce_slots(const double* stats_rows_dev, const double* hist_rows_dev, const int64_t* row_begin_host,
+                       int n_out, int ncols, double* packed_dev, void* scratch_dev, void* stream);
+/* hepmc_vegas_update_grid on packed slot rows (n_slots, 3 + ndim*K), e.g. the all-gather receive buffer. */
+int hepmc_vegas_update_grid_packed(const double* packed_dev, int n_slots, double* grid_dev, int ndim, int divisions,
+                                   double c, int j, double* est_var_dev, void* stream);
+
 /* Workspace (bytes) hepmc_vegas_integrate needs for n points per iteration. */
 int64_t hepmc_vegas_workspace_bytes(int ndim, int divisions, int64_t n);
 /* Whole single-GPU VegasMC.__call__ (vegas.py:74-118): `iterations` x (sample, slot
