@@ -79,10 +79,11 @@ SIGNATURES = {
     "hepmc_rambo_pdf": (_dbl, [_int, _dbl]),
     "hepmc_rwm_chains": (_int, [_dens_p, _vp, _int, ctypes.POINTER(_dbl), _i64, _i64, _i64, _i64, _u64, _u32,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "hepmc_hmc_chains": (_int, [_dens_p, _elm_p, _int, _vp, ctypes.POINTER(_dbl), _dbl, _int,
+    "hepmc_leapfrog": (_int, [_dens_p, _elm_p, _int, _int, ctypes.POINTER(_dbl), _dbl, _int, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "hepmc_hmc_chains": (_int, [_dens_p, _elm_p, _int, _int, _vp, ctypes.POINTER(_dbl), _dbl, _int,
                                 _i64, _i64, _i64, _i64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "hepmc_mc3_chains": (_int, [_dens_p, _vp, _int, _dbl, _int, ctypes.POINTER(_dbl), _dbl, _int, _elm_p, _int, _vp,
-                                _i64, _i64, _i64, _i64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hepmc_mc3_chains": (_int, [_dens_p, _vp, _int, _dbl, _int, ctypes.POINTER(_dbl), _dbl, _int, _elm_p, _int, _int, _vp,
+                                _i64, _i64, _i64, _i64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hepmc_elm_eval": (_int, [_elm_p, _int, _int, _int, _vp, _i64, _vp, _vp]),
     "hepmc_gather_rows": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
     "hepmc_autocov": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _i64, _i64, _vp, _vp]),

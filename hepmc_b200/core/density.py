@@ -202,4 +202,7 @@ def as_builtin(fn):
             return None
     if "pdf" in vars(obj):
         return None
+    # a user subclass that overrides pdf at class level must not be fused as its analytic parent
+    if not type(obj).__module__.startswith("hepmc_b200.") and type(obj).pdf is not BuiltinDensity.pdf:
+        return None
     return obj

@@ -107,8 +107,8 @@ class VegasMC(object):
         # they are, read in place by the grid update (no slicing or copying between the three)
         slot_local = torch.zeros((n_slots_local, 3 + cols), dtype=torch.float64, device=dev)
         slots_all = slot_local if ws == 1 else torch.empty((_lib.N_SLOTS, 3 + cols), dtype=torch.float64, device=dev)
-        scratch = torch.empty(int(_lib.load().hepmc_reduce_slots_scratch_bytes(n_slots_local, cols)) // 8 + 1,
-                              dtype=torch.float64, device=dev)
+        scratch = torch.zeros(int(_lib.load().hepmc_reduce_slots_scratch_bytes(n_slots_local, cols)) // 8 + 1,
+                              dtype=torch.float64, device=dev)    # zero: arrival counters of the fused reduction
         begins_c = _lib.i64_array(begins)
         seed = rng.get_seed()
         sid0 = rng.next_stream(iterations)

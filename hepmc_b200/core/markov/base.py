@@ -52,7 +52,7 @@ class MarkovUpdate(object):
             "HamiltonianUpdate over built-in densities; it has no host-side step loop (no CPU fallback).")
 
     def sample(self, sample_size, initial, out_mask=None, log_every=5000,
-               thin=1, store_chain=True, first_chain=0, replay=None):
+               thin=1, store_chain=True, first_chain=0, replay=None, total_chains=None):
         """Generate `sample_size` states per chain (the first is `initial`).
 
         :param initial: (ndim,) for one chain -> data (sample_size, ndim) like the reference;
@@ -62,9 +62,14 @@ class MarkovUpdate(object):
         :param thin: keep every thin-th state (t = 0, thin, 2 thin, ...).
         :param store_chain: False -> keep only the final states (data has one state per chain).
         :param first_chain: global index of chain 0 (Philox counter; sharding over GPUs).
-        :param replay: (z, u) tapes consumed instead of the native generator."""
+        :param replay: (z, u) tapes consumed instead of the native generator.
+        :param total_chains: size of the WHOLE ensemble when `initial` is one shard of it (several
+            calls or GPUs); selects the kernel layout of surrogate-gradient updates so that a chain
+            does not depend on the sharding.  Default: the sum over the torch.distributed group,
+            else the size of `initial`."""
         from .ensemble import prepare_initial
         x0, is_ensemble = prepare_initial(initial, self.ndim)
+        self._total_chains = total_chains
         chain, last, accepted, total = self._run_ensemble(
             x0, int(sample_size), int(thin), bool(store_chain), int(first_chain), replay)
         data = chain if store_chain else last[:, None, :]

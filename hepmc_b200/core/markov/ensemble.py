@@ -77,8 +77,25 @@ def run_rwm(blk, x0, proposal_kind, prop_param, sample_size, thin=1, store_chain
     return chain, last, accepted, total
 
 
+def coop_flag(n_local, nodes, total_chains=None):
+    """The `coop` argument of hepmc_hmc_chains / hepmc_mc3_chains / hepmc_leapfrog (1 = one CTA per chain,
+    0 = one chain per thread), decided from the GLOBAL ensemble size so that the same chain runs the
+    same kernel -- hence the same arithmetic -- however the ensemble is sharded over calls or GPUs:
+    `total_chains` if the caller states it, else the sum of the local counts over the process group,
+    else the local count.  Threshold: csrc/chains.cuh coop_max_chains (8 * nodes in [1024, 8192])."""
+    if total_chains is None:
+        from ... import parallel
+        rank, ws = parallel.world()
+        total_chains = n_local
+        if ws > 1:
+            t = torch.tensor([n_local], dtype=torch.int64, device=_lib.device())
+            total_chains = int(parallel.sum_int(t).item())
+    limit = min(max(8 * int(nodes), 1024), 8192)
+    return 1 if int(total_chains) <= limit else 0
+
+
 def run_hmc(blk, elm_blk, precision, x0, mass_diag, step_size, steps, sample_size, thin=1, store_chain=True,
-            first_chain=0, stream_id=None, replay=None):
+            first_chain=0, stream_id=None, replay=None, total_chains=None):
     dev = x0.device
     n_chains, ndim = x0.shape
     chain, last, accepted, total = alloc_outputs(n_chains, ndim, sample_size, thin, store_chain, dev)
@@ -89,8 +106,9 @@ def run_hmc(blk, elm_blk, precision, x0, mass_diag, step_size, steps, sample_siz
         if tuple(p.shape) != (n_chains, sample_size - 1, ndim) or tuple(u.shape) != (n_chains, sample_size - 1):
             raise ValueError("replay tapes must be (C, T-1, ndim) and (C, T-1)")
     sid = rng.next_stream() if stream_id is None else stream_id
+    coop = coop_flag(n_chains, elm_blk.nodes, total_chains) if elm_blk is not None else 0
     _lib.call("hepmc_hmc_chains", ctypes.byref(blk), ctypes.byref(elm_blk) if elm_blk is not None else None,
-              int(precision), _lib.ptr(x0), _lib.dbl_array(mass_diag), float(step_size), int(steps),
+              int(precision), coop, _lib.ptr(x0), _lib.dbl_array(mass_diag), float(step_size), int(steps),
               n_chains, int(first_chain), int(sample_size), int(thin), rng.get_seed(), sid,
               _lib.ptr(p), _lib.ptr(u), _lib.ptr(chain), _lib.ptr(last), _lib.ptr(accepted), _lib.ptr(total),
               _lib.stream_ptr())
@@ -182,9 +200,11 @@ def run_rwm_generic(pdf_fn, x0, proposal_kind, prop_param, sample_size, thin=1, 
 
 
 def run_hmc_generic(pdf_fn, grad_fn, x0, mass_diag, step_size, steps, sample_size, thin=1, store_chain=True,
-                    first_chain=0):
+                    first_chain=0, simulate=None):
     """HamiltonianUpdate over a user-defined target: leapfrog of simulation.py:34-42 with the user's
-    pot_gradient, momentum ~ N(0, diag(mass)), acceptance of hmc.py:54-59."""
+    pot_gradient, momentum ~ N(0, diag(mass)), acceptance of hmc.py:54-59.  `simulate`: a user-supplied
+    simulator (hmc.py:25-27 `simulate=` / `sim_class=`), called as simulate(q, p) on (C, ndim) CUDA
+    tensors instead of the built-in loop; rows it returns non-finite are rejected (hmc.py:77-78)."""
     dev = x0.device
     C, ndim = x0.shape
     chain, last, accepted, total = alloc_outputs(C, ndim, sample_size, thin, store_chain, dev)
@@ -195,7 +215,7 @@ def run_hmc_generic(pdf_fn, grad_fn, x0, mass_diag, step_size, steps, sample_siz
     pdf = _user_values(pdf_fn, state, "pdf").reshape(C)
     if chain is not None:
         chain[:, 0] = state
-    half = step_size / 2
+    half = step_size / 2 if step_size is not None else None
 
     def grad(q):
         return _user_values(grad_fn, q, "pot_gradient").reshape(C, ndim)
@@ -204,13 +224,23 @@ def run_hmc_generic(pdf_fn, grad_fn, x0, mass_diag, step_size, steps, sample_siz
         u = _step_draws(C, 2 * npair + 1, first_chain, sid0 + t - 1, dev)
         p0 = torch.sqrt(mass) * _normals(u, ndim)
         q, p = state.clone(), p0.clone()
-        g = grad(q)
-        for _ in range(int(steps)):
-            p = p - half * g
-            q = q + step_size * (p / mass)
+        if simulate is not None:
+            out = simulate(q, p)
+            if out is None or out[0] is None:
+                q, p = torch.full_like(state, float("nan")), torch.full_like(state, float("nan"))
+            else:
+                q = _user_values(lambda _x: out[0], q, "simulate").reshape(C, ndim)
+                p = _user_values(lambda _x: out[1], p, "simulate").reshape(C, ndim)
+        else:
             g = grad(q)
-            p = p - half * g
+            for _ in range(int(steps)):
+                p = p - half * g
+                q = q + step_size * (p / mass)
+                g = grad(q)
+                p = p - half * g
         cpdf = _user_values(pdf_fn, q, "pdf").reshape(C)
+        if simulate is not None:
+            cpdf = torch.where(torch.isfinite(q).all(dim=1), cpdf, torch.zeros_like(cpdf))   # q is None -> pdf = 0
         # N(p) / N(p0) for the diagonal Gaussian momentum distribution
         kin = torch.exp(-0.5 * ((p * p - p0 * p0) / mass).sum(dim=1))
         prob = cpdf * kin / pdf

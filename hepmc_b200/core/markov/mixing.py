@@ -19,7 +19,7 @@ from ... import _lib, rng
 from . import ensemble
 
 
-def run_mc3(dens, channels, beta, local, x0, sample_size, thin, store_chain, first_chain, replay):
+def run_mc3(dens, channels, beta, local, x0, sample_size, thin, store_chain, first_chain, replay, total_chains=None):
     """Launch hepmc_mc3_chains.  `local` is None (beta == 1), a DefaultMetropolis with a Gaussian or
     UniformLocal proposal, or a HamiltonianUpdate."""
     from ...hamiltonian.hmc import HamiltonianUpdate
@@ -30,6 +30,7 @@ def run_mc3(dens, channels, beta, local, x0, sample_size, thin, store_chain, fir
     n_chains, ndim = x0.shape
     chain, last, accepted, total = ensemble.alloc_outputs(n_chains, ndim, sample_size, thin, store_chain, dev)
     local_kind, scale, step_size, steps, elm_blk, keep, prec = 0, None, 0.0, 0, None, None, 0
+    counted = None
     if local is None:
         if beta < 1.0:
             raise TypeError("a local update is needed when beta < 1")
@@ -41,7 +42,10 @@ def run_mc3(dens, channels, beta, local, x0, sample_size, thin, store_chain, fir
         local_kind, scale = 1, local.p_dist._diag()
         step_size, steps = float(local.step_size), int(local.steps)
         grad = vars(dens).get("pot_gradient", None)
+        counted = grad if hasattr(grad, "count") and hasattr(grad, "fn") else None   # util.count_calls wrapper
         grad = getattr(grad, "fn", grad)
+        if getattr(grad, "__self__", None) is dens and getattr(grad, "__func__", None) is type(dens).pot_gradient:
+            grad = None                             # the density's own gradient behind util.count_calls
         if grad is not None:
             if not isinstance(grad, SurrogateGradient):
                 raise TypeError("a replaced pot_gradient must be a surrogate.SurrogateGradient")
@@ -65,12 +69,18 @@ def run_mc3(dens, channels, beta, local, x0, sample_size, thin, store_chain, fir
         if tuple(draw.shape) != (n_chains, sample_size - 1, ndim):
             raise ValueError("replay tapes must be (C, T-1), (C, T-1, ndim), (C, T-1)")
     table = channels._table()
+    n_local = torch.zeros(1, dtype=torch.int64, device=dev) if counted is not None else None
+    coop = ensemble.coop_flag(n_chains, elm_blk.nodes, total_chains) if elm_blk is not None else 0
     _lib.call("hepmc_mc3_chains", ctypes.byref(dens._block()), _lib.ptr(table), channels.count, float(beta),
               local_kind, _lib.dbl_array(scale) if scale is not None else None, step_size, steps,
-              ctypes.byref(elm_blk) if elm_blk is not None else None, prec, _lib.ptr(x0),
+              ctypes.byref(elm_blk) if elm_blk is not None else None, prec, coop, _lib.ptr(x0),
               n_chains, int(first_chain), int(sample_size), int(thin), rng.get_seed(), rng.next_stream(),
               _lib.ptr(sel), _lib.ptr(draw), _lib.ptr(u),
-              _lib.ptr(chain), _lib.ptr(last), _lib.ptr(accepted), _lib.ptr(total), _lib.stream_ptr())
+              _lib.ptr(chain), _lib.ptr(last), _lib.ptr(accepted), _lib.ptr(total), _lib.ptr(n_local), _lib.stream_ptr())
+    if counted is not None:
+        # util.count_calls(target, 'pot_gradient') (interfaces/mc3_hmc_el.py:35): the kernel evaluates the
+        # gradient steps + 1 times per local HMC update (simulation.py:34-42, one row per call)
+        counted.count += int(n_local.item()) * (steps + 1)
     del keep
     return chain, last, accepted, total
 
@@ -116,4 +126,4 @@ class MixingMarkovUpdate(MarkovUpdate):
             return ensemble.run_mixing_generic(is_upd.pdf, channels, float(self.weights[0]), local, x0, sample_size,
                                                thin, store_chain, first_chain)
         return run_mc3(dens, channels, float(self.weights[0]), local, x0, sample_size, thin, store_chain,
-                       first_chain, replay)
+                       first_chain, replay, getattr(self, "_total_chains", None))

@@ -124,7 +124,6 @@ __global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ Dens d
     const PhiloxKey key = philox_expand(a.seed);
     constexpr int NCALL = (NDIM + 1) / 2;
     constexpr uint32_t CPS = NCALL + 1;
-    const double half_eps = a.step_size / 2;
     int64_t acc = 0;
     if (active) {
         const uint64_t g = (uint64_t)(a.first_chain + c);
@@ -134,7 +133,7 @@ __global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ Dens d
         double pdf = density_pdf_n<NDIM>(dens, x);
         if (a.chain && writer) store_state<NDIM>(a.chain, c, a.n_kept, 0, x);
         for (int64_t t = 1; t < a.T; ++t) {
-            double p0[NDIM], q[NDIM], p[NDIM], grad[NDIM];
+            double p0[NDIM], q[NDIM], p[NDIM];
             if (a.z_replay) {
                 const double* z = a.z_replay + ((size_t)c * (a.T - 1) + (t - 1)) * NDIM;
 #pragma unroll
@@ -152,17 +151,7 @@ __global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ Dens d
             }
 #pragma unroll
             for (int d = 0; d < NDIM; ++d) { q[d] = x[d]; p[d] = p0[d]; }
-            // leapfrog, simulation.py:36-42
-            gradient(q, grad);
-            for (int s = 0; s < a.steps; ++s) {
-#pragma unroll
-                for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
-#pragma unroll
-                for (int d = 0; d < NDIM; ++d) q[d] += a.step_size * (pdist.c[d] * (p[d] - pdist.a[d]));
-                gradient(q, grad);
-#pragma unroll
-                for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
-            }
+            leapfrog_steps<NDIM>(gradient, pdist, q, p, a.step_size, a.steps);   // simulation.py:34-42
             const double cpdf = density_pdf_n<NDIM>(dens, q);              // hmc.py:80
             const double np1 = density_pdf_n<NDIM>(pdist, p);
             const double np0 = density_pdf_n<NDIM>(pdist, p0);
@@ -194,6 +183,86 @@ __global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ Dens d
         }
     }
     finish_counts(a, active && writer, c, acc);
+}
+
+// ------------------------------------------------------------------ HamiltonLeapfrog.__call__, batched
+// simulation.py:26-46 for n independent (q, p) states: thread-per-state, or ONE CTA per state (COOP) with the
+// node sum of a surrogate gradient split over the threads -- the same two layouts as hmc_kernel.
+struct LeapArgs {
+    const double* q_in;
+    const double* p_in;
+    double* q_out;
+    double* p_out;
+    int64_t n;
+    double step_size;
+    int steps;
+};
+
+template <int NDIM, class T, bool COOP = false>
+__global__ void __launch_bounds__(128) leapfrog_kernel(const __grid_constant__ Dens dens,
+                                                       const __grid_constant__ Dens pdist,
+                                                       const __grid_constant__ hepmc_elm_t elm,
+                                                       const __grid_constant__ LeapArgs a) {
+    extern __shared__ double smem_raw[];
+    __shared__ double s_red[COOP ? (kCoopThreads / 32) * NDIM : 1];
+    T* tab = reinterpret_cast<T*>(smem_raw);
+    const bool use_elm = elm.mode != HEPMC_GRAD_EXACT;
+    if (use_elm) {
+        elm_stage_tables<T>(elm, NDIM, tab);
+        __syncthreads();
+    }
+    const int64_t c = COOP ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n) return;        // COOP: the whole CTA leaves together
+    auto gradient = [&](const double (&q)[NDIM], double (&grad)[NDIM]) {
+        if (use_elm) {
+            if constexpr (COOP) {
+                elm_gradient<NDIM, T>(elm.mode, elm.nodes, tab, q, grad, (int)threadIdx.x, kCoopThreads);
+                coop_sum<NDIM>(grad, s_red);
+            } else {
+                elm_gradient<NDIM, T>(elm.mode, elm.nodes, tab, q, grad);
+            }
+        } else {
+            density_pot_gradient_n<NDIM>(dens, q, grad);
+        }
+    };
+    double q[NDIM], p[NDIM];
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) { q[d] = a.q_in[c * NDIM + d]; p[d] = a.p_in[c * NDIM + d]; }
+    leapfrog_steps<NDIM>(gradient, pdist, q, p, a.step_size, a.steps);
+    if (!COOP || threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) { a.q_out[c * NDIM + d] = q[d]; a.p_out[c * NDIM + d] = p[d]; }
+    }
+}
+
+// momentum distribution Gaussian(0, diag(mass)) as a density block: gaussian.py:30-51,73-76
+static int fill_momentum_dist(Dens& pd, int nd, const double* mass_host, const char* who) {
+    pd = Dens{};
+    pd.kind = HEPMC_GAUSSIAN; pd.ndim = nd;
+    double logdet = 0.0;
+    for (int d = 0; d < nd; ++d) {
+        HEPMC_REQUIRE(mass_host[d] > 0.0, HEPMC_E_ARG, "%s: mass must be positive", who);
+        pd.a[d] = 0.0; pd.b[d] = sqrt(1.0 / mass_host[d]); pd.c[d] = 1.0 / mass_host[d];
+        logdet += log(mass_host[d]);
+    }
+    pd.s1 = nd * log(2.0 * 3.141592653589793) + logdet;
+    return 0;
+}
+
+static int check_elm(hepmc_elm_t& el, const hepmc_elm_t* elm, const Dens& dens, const char* who) {
+    el = hepmc_elm_t{};
+    el.mode = HEPMC_GRAD_EXACT;
+    if (elm != nullptr && elm->mode != HEPMC_GRAD_EXACT) {
+        HEPMC_REQUIRE(elm->mode == HEPMC_GRAD_ELM_GAUSS || elm->mode == HEPMC_GRAD_ELM_TRIG, HEPMC_E_ARG,
+                      "%s: bad surrogate mode %d", who, elm->mode);
+        HEPMC_REQUIRE(elm->nodes >= 1 && elm->p0_dev && elm->p1_dev && elm->out_w_dev, HEPMC_E_ARG,
+                      "%s: incomplete surrogate parameters", who);
+        el = *elm;
+    } else {
+        HEPMC_REQUIRE(!(dens.kind == HEPMC_BANANA && dens.ndim != 2), HEPMC_E_UNSUPPORTED,
+                      "Banana.pot_gradient exists for ndim == 2 only (banana.py:44-51)");
+    }
+    return 0;
 }
 
 static int fill_chain_args(ChainArgs& a, const char* who, int ndim, const double* x0_dev, const double* scale_host,
@@ -259,7 +328,7 @@ int hepmc_rwm_chains(const hepmc_density_t* dens, const double* x0_dev, int prop
     return 0;
 }
 
-int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int precision,
+int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int precision, int coop_flag,
                      const double* x0_dev, const double* mass_host, double step_size, int steps,
                      int64_t n_chains, int64_t first_chain, int64_t sample_size, int64_t thin,
                      uint64_t seed, uint32_t stream_id,
@@ -278,28 +347,12 @@ int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int pr
                             total_accepted_dev);
     if (e) return e;
     a.step_size = step_size; a.steps = steps; a.precision = precision;
-    hepmc_elm_t el{};
-    el.mode = HEPMC_GRAD_EXACT;
-    if (elm != nullptr && elm->mode != HEPMC_GRAD_EXACT) {
-        HEPMC_REQUIRE(elm->mode == HEPMC_GRAD_ELM_GAUSS || elm->mode == HEPMC_GRAD_ELM_TRIG, HEPMC_E_ARG,
-                      "hepmc_hmc_chains: bad surrogate mode %d", elm->mode);
-        HEPMC_REQUIRE(elm->nodes >= 1 && elm->p0_dev && elm->p1_dev && elm->out_w_dev, HEPMC_E_ARG,
-                      "hepmc_hmc_chains: incomplete surrogate parameters");
-        el = *elm;
-    } else {
-        HEPMC_REQUIRE(!(dens->kind == HEPMC_BANANA && nd != 2), HEPMC_E_UNSUPPORTED,
-                      "Banana.pot_gradient exists for ndim == 2 only (banana.py:44-51)");
-    }
-    // momentum distribution Gaussian(0, diag(mass)): gaussian.py:30-51,73-76
-    Dens pd{};
-    pd.kind = HEPMC_GAUSSIAN; pd.ndim = nd;
-    double logdet = 0.0;
-    for (int d = 0; d < nd; ++d) {
-        HEPMC_REQUIRE(mass_host[d] > 0.0, HEPMC_E_ARG, "hepmc_hmc_chains: mass must be positive");
-        pd.a[d] = 0.0; pd.b[d] = sqrt(1.0 / mass_host[d]); pd.c[d] = 1.0 / mass_host[d];
-        logdet += log(mass_host[d]);
-    }
-    pd.s1 = nd * log(2.0 * 3.141592653589793) + logdet;
+    hepmc_elm_t el;
+    e = check_elm(el, elm, *dens, "hepmc_hmc_chains");
+    if (e) return e;
+    Dens pd;
+    e = fill_momentum_dist(pd, nd, mass_host, "hepmc_hmc_chains");
+    if (e) return e;
     if (n_chains == 0) return 0;
     cudaStream_t st = as_stream(stream);
     if (precision >= 2 && el.mode != HEPMC_GRAD_EXACT) {
@@ -317,10 +370,9 @@ int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int pr
     size_t smem = el.mode == HEPMC_GRAD_EXACT ? 0 : (size_t)el.nodes * elm_row(nd) * esz;
     HEPMC_REQUIRE(smem <= (size_t)maxs, HEPMC_E_UNSUPPORTED,
                   "hepmc_hmc_chains: %d surrogate nodes do not fit shared memory (%zu > %d bytes)", el.nodes, smem, maxs);
-    // small ensembles with a surrogate gradient: one CTA per chain (see hmc_kernel<.., COOP>); the
-    // threshold is a property of the CALL (its local chain count), results of the two kernels differ
-    // in the last bits of the gradient sums
-    const bool coop = el.mode != HEPMC_GRAD_EXACT && n_chains <= coop_max_chains(el.nodes);
+    // small ensembles with a surrogate gradient: one CTA per chain (see hmc_kernel<.., COOP>); the caller
+    // chooses (coop = 0 / 1) or leaves it to the chain count of this call (coop = -1), see use_coop
+    const bool coop = use_coop(coop_flag, el.mode != HEPMC_GRAD_EXACT, n_chains, el.nodes);
     const unsigned cblocks = (unsigned)n_chains;
 #define HMC_LAUNCH(ND, TT, CO, NB)                                                                         \
     do {                                                                                                   \
@@ -338,6 +390,58 @@ int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int pr
     HEPMC_DISPATCH_NDIM(nd, HMC_CASE);
 #undef HMC_CASE
 #undef HMC_LAUNCH
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+int hepmc_leapfrog(const hepmc_density_t* dens, const hepmc_elm_t* elm, int precision, int coop_flag,
+                   const double* mass_host, double step_size, int steps, int64_t n,
+                   const double* q_dev, const double* p_dev, double* q_out_dev, double* p_out_dev, void* stream) {
+    HEPMC_REQUIRE(dens != nullptr && mass_host != nullptr, HEPMC_E_ARG, "hepmc_leapfrog: NULL dens/mass");
+    HEPMC_REQUIRE(dens->kind >= HEPMC_CAMEL && dens->kind <= HEPMC_UNIFORM, HEPMC_E_ARG,
+                  "hepmc_leapfrog: the potential must belong to a built-in density (kind %d)", dens->kind);
+    const int nd = dens->ndim;
+    HEPMC_REQUIRE(nd >= 1 && nd <= HEPMC_MAX_CHAIN_DIM, HEPMC_E_UNSUPPORTED, "hepmc_leapfrog: ndim %d outside [1,%d]", nd,
+                  HEPMC_MAX_CHAIN_DIM);
+    HEPMC_REQUIRE(steps >= 0 && n >= 0, HEPMC_E_ARG, "hepmc_leapfrog: negative steps / n");
+    HEPMC_REQUIRE(precision == 0 || precision == 1, HEPMC_E_UNSUPPORTED,
+                  "hepmc_leapfrog: precision must be 0 (float64) or 1 (float32 surrogate arithmetic)");
+    hepmc_elm_t el;
+    int e = check_elm(el, elm, *dens, "hepmc_leapfrog");
+    if (e) return e;
+    Dens pd;
+    e = fill_momentum_dist(pd, nd, mass_host, "hepmc_leapfrog");
+    if (e) return e;
+    if (n == 0) return 0;
+    HEPMC_REQUIRE(q_dev && p_dev && q_out_dev && p_out_dev, HEPMC_E_ARG, "hepmc_leapfrog: NULL state buffer");
+    if (el.mode == HEPMC_GRAD_EXACT) precision = 0;
+    LeapArgs a{q_dev, p_dev, q_out_dev, p_out_dev, n, step_size, steps};
+    int dev = 0, maxs = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&maxs, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const size_t esz = precision == 0 ? 8 : 4;
+    const size_t smem = el.mode == HEPMC_GRAD_EXACT ? 0 : (size_t)el.nodes * elm_row(nd) * esz;
+    HEPMC_REQUIRE(smem <= (size_t)maxs, HEPMC_E_UNSUPPORTED,
+                  "hepmc_leapfrog: %d surrogate nodes do not fit shared memory (%zu > %d bytes)", el.nodes, smem, maxs);
+    const bool coop = use_coop(coop_flag, el.mode != HEPMC_GRAD_EXACT, n, el.nodes);
+    const unsigned blocks = coop ? (unsigned)n : (unsigned)((n + 127) / 128);
+    cudaStream_t st = as_stream(stream);
+#define LEAP_LAUNCH(ND, TT, CO)                                                                            \
+    do {                                                                                                   \
+        HEPMC_CUDA(cudaFuncSetAttribute(leapfrog_kernel<ND, TT, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        leapfrog_kernel<ND, TT, CO><<<blocks, 128, smem, st>>>(*dens, pd, el, a);                          \
+    } while (0)
+#define LEAP_CASE(ND)                                                                                      \
+    do {                                                                                                   \
+        if (precision == 0) {                                                                              \
+            if (coop) LEAP_LAUNCH(ND, double, true); else LEAP_LAUNCH(ND, double, false);                  \
+        } else {                                                                                           \
+            if (coop) LEAP_LAUNCH(ND, float, true); else LEAP_LAUNCH(ND, float, false);                    \
+        }                                                                                                  \
+    } while (0)
+    HEPMC_DISPATCH_NDIM(nd, LEAP_CASE);
+#undef LEAP_CASE
+#undef LEAP_LAUNCH
     HEPMC_LAUNCH_CHECK();
     return 0;
 }

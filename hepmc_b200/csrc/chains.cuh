@@ -81,11 +81,39 @@ __device__ __forceinline__ void coop_sum(double (&g)[NDIM], double* red) {
     }
 }
 
+// HamiltonLeapfrog.__call__, simulation.py:34-42, for one state held in registers: un-merged half steps,
+// steps + 1 gradient evaluations; kin_gradient = Gaussian(mean, diag mass).pot_gradient = (p - mean)/mass
+// (gaussian.py:45-47).  Shared by hmc_kernel, mc3_kernel's local HMC update and leapfrog_kernel
+// (hepmc_leapfrog), so the three run the same arithmetic.
+template <int NDIM, class GradFn>
+__device__ __forceinline__ void leapfrog_steps(GradFn& gradient, const Dens& pdist, double (&q)[NDIM], double (&p)[NDIM],
+                                               double step_size, int steps) {
+    const double half_eps = step_size / 2;
+    double grad[NDIM];
+    gradient(q, grad);
+    for (int s = 0; s < steps; ++s) {
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) q[d] += step_size * (pdist.c[d] * (p[d] - pdist.a[d]));
+        gradient(q, grad);
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
+    }
+}
+
 // Ensembles up to this many chains per call run the cooperative HMC kernel.  Measured crossover of
 // the total throughput (scripts/coop_perf.py, camel-8D, 20 leapfrog): ~12 000 chains at 1024 nodes,
 // ~2000-3700 at 100 nodes; below it the cooperative kernel is up to 48x faster per chain
 // (one chain, 1024 nodes, float64: 2.3e4 instead of 4.8e2 steps/s).  Development override:
 // HEPMC_HMC_COOP_MAX.
+// `coop` argument of the C ABI: 1 / 0 force the cooperative / the thread-per-chain kernel, -1 decides from
+// the chain count OF THIS CALL.  The two kernels add the node terms of the surrogate gradient in
+// different orders (last-bit differences that an accept/reject eventually amplifies), so a caller that
+// shards one ensemble over several calls or GPUs must pass 0 or 1 -- the Python mirror decides from
+// the GLOBAL ensemble size (core/markov/ensemble.py coop_flag).
+inline bool use_coop(int coop, bool has_elm, int64_t n_chains, int nodes);
+
 inline int64_t coop_max_chains(int nodes) {
     static int64_t forced = -2;
     if (forced == -2) {
@@ -95,6 +123,12 @@ inline int64_t coop_max_chains(int nodes) {
     if (forced >= 0) return forced;
     const int64_t v = 8 * (int64_t)nodes;
     return v < 1024 ? 1024 : (v > 8192 ? 8192 : v);
+}
+
+inline bool use_coop(int coop, bool has_elm, int64_t n_chains, int nodes) {
+    if (!has_elm) return false;
+    if (coop >= 0) return coop != 0;
+    return n_chains <= coop_max_chains(nodes);
 }
 
 // tensor-core launchers (elm_tc.cu)

@@ -167,11 +167,34 @@ __global__ void __launch_bounds__(kHistLanes * kHistCols) reduce_hist_kernel(con
 constexpr int kSlotGroups = 32;
 constexpr int kRedCols = 32, kRedLanes = 8;
 
-__global__ void __launch_bounds__(kRedCols * kRedLanes) reduce_slots_l1_kernel(
+// level 2 of slot s, run by the LAST level-1 CTA of the slot to finish (threadfence + counter): one launch,
+// and the combine order is fixed whichever CTA runs it.
+__device__ __forceinline__ void reduce_slots_l2(const double* __restrict__ in /* (G, 3 + ncols) */, int ncols,
+                                                double* __restrict__ out /* (3 + ncols) */) {
+    const int row = 3 + ncols;
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+        double acc = 0.0;
+#pragma unroll 8
+        for (int g = 0; g < kSlotGroups; ++g) acc += __ldcg(in + (size_t)g * row + 3 + c);
+        out[3 + c] = acc;
+    }
+    if (threadIdx.x == 0) {
+        Stats t{0.0, 0.0, 0.0};
+        for (int g = 0; g < kSlotGroups; ++g) {
+            Stats u{__ldcg(in + (size_t)g * row), __ldcg(in + (size_t)g * row + 1), __ldcg(in + (size_t)g * row + 2)};
+            t = merge(t, u);
+        }
+        out[0] = t.n; out[1] = t.mean; out[2] = t.m2;
+    }
+}
+
+__global__ void __launch_bounds__(kRedCols * kRedLanes) reduce_slots_kernel(
     const double* __restrict__ stats_rows, const double* __restrict__ hist_rows, const __grid_constant__ RowRanges rr,
-    int ncols, double* __restrict__ scratch /* (n_out, G, 3 + ncols) */) {
+    int ncols, double* __restrict__ scratch /* (n_out, G, 3 + ncols) */, unsigned int* __restrict__ counters /* n_out, zero */,
+    double* __restrict__ packed /* (n_out, 3 + ncols) */) {
     __shared__ double part[kRedLanes][kRedCols];
     __shared__ Stats s_w[8];
+    __shared__ bool s_last;
     const int s = blockIdx.z, g = blockIdx.y;
     const int64_t b = rr.begin[s], len = rr.begin[s + 1] - b;
     const int64_t r0 = b + len * g / kSlotGroups, r1 = b + len * (g + 1) / kSlotGroups;
@@ -185,42 +208,34 @@ __global__ void __launch_bounds__(kRedCols * kRedLanes) reduce_slots_l1_kernel(
         }
         const Stats total = block_merge<kRedCols * kRedLanes>(acc, s_w);
         if (threadIdx.x == 0) { out[0] = total.n; out[1] = total.mean; out[2] = total.m2; }
-        return;
-    }
-    const int cx = threadIdx.x % kRedCols, ry = threadIdx.x / kRedCols;
-    const int col = blockIdx.x * kRedCols + cx;
-    double acc = 0.0;
-    if (col < ncols)
-        for (int64_t r = r0 + ry; r < r1; r += kRedLanes) acc += hist_rows[r * ncols + col];
-    part[ry][cx] = acc;
-    __syncthreads();
-#pragma unroll
-    for (int half = kRedLanes / 2; half > 0; half >>= 1) {
-        if (ry < half) part[ry][cx] += part[ry + half][cx];
-        __syncthreads();
-    }
-    if (ry == 0 && col < ncols) out[3 + col] = part[0][cx];
-}
-
-__global__ void __launch_bounds__(256) reduce_slots_l2_kernel(const double* __restrict__ scratch, int ncols,
-                                                              double* __restrict__ packed /* (n_out, 3 + ncols) */) {
-    const int s = blockIdx.x;
-    const int row = 3 + ncols;
-    const double* in = scratch + (size_t)s * kSlotGroups * row;
-    double* out = packed + (size_t)s * row;
-    for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+    } else {
+        const int cx = threadIdx.x % kRedCols, ry = threadIdx.x / kRedCols;
+        const int col = blockIdx.x * kRedCols + cx;
         double acc = 0.0;
-#pragma unroll 8
-        for (int g = 0; g < kSlotGroups; ++g) acc += in[(size_t)g * row + 3 + c];
-        out[3 + c] = acc;
-    }
-    if (threadIdx.x == 0) {
-        Stats t{0.0, 0.0, 0.0};
-        for (int g = 0; g < kSlotGroups; ++g) {
-            Stats u{in[(size_t)g * row], in[(size_t)g * row + 1], in[(size_t)g * row + 2]};
-            t = merge(t, u);
+        if (col < ncols)
+            for (int64_t r = r0 + ry; r < r1; r += kRedLanes) acc += hist_rows[r * ncols + col];
+        part[ry][cx] = acc;
+        __syncthreads();
+#pragma unroll
+        for (int half = kRedLanes / 2; half > 0; half >>= 1) {
+            if (ry < half) part[ry][cx] += part[ry + half][cx];
+            __syncthreads();
         }
-        out[0] = t.n; out[1] = t.mean; out[2] = t.m2;
+        if (ry == 0 && col < ncols) out[3 + col] = part[0][cx];
+    }
+    // last CTA of the slot: combine the groups
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int total = (unsigned int)(ntile + 1) * kSlotGroups;
+        const unsigned int prev = atomicAdd(counters + s, 1u);
+        s_last = (prev == total - 1);
+        if (s_last) counters[s] = 0u;     // ready for the next call on the same scratch
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        reduce_slots_l2(scratch + (size_t)s * kSlotGroups * (3 + ncols), ncols, packed + (size_t)s * (3 + ncols));
     }
 }
 
@@ -554,7 +569,7 @@ int hepmc_vegas_update_grid(const double* slot_stats_dev, const double* slot_his
 }
 
 int64_t hepmc_reduce_slots_scratch_bytes(int n_out, int ncols) {
-    return (int64_t)n_out * kSlotGroups * (3 + ncols) * 8;
+    return (int64_t)n_out * kSlotGroups * (3 + ncols) * 8 + 256;   // group partials + per-slot arrival counters
 }
 
 int hepmc_reduce_slots(const double* stats_rows_dev, const double* hist_rows_dev, const int64_t* row_begin_host,
@@ -566,10 +581,10 @@ int hepmc_reduce_slots(const double* stats_rows_dev, const double* hist_rows_dev
                   "hepmc_reduce_slots: bad arguments");
     const int ntile = (ncols + kRedCols - 1) / kRedCols;
     dim3 grid(ntile + 1, kSlotGroups, n_out);
-    reduce_slots_l1_kernel<<<grid, kRedCols * kRedLanes, 0, as_stream(stream)>>>(
-        stats_rows_dev, hist_rows_dev, rr, ncols, reinterpret_cast<double*>(scratch_dev));
-    reduce_slots_l2_kernel<<<n_out, 256, 0, as_stream(stream)>>>(reinterpret_cast<const double*>(scratch_dev), ncols,
-                                                                 packed_dev);
+    double* partials = reinterpret_cast<double*>(scratch_dev);
+    unsigned int* counters = reinterpret_cast<unsigned int*>(partials + (size_t)n_out * kSlotGroups * (3 + ncols));
+    reduce_slots_kernel<<<grid, kRedCols * kRedLanes, 0, as_stream(stream)>>>(stats_rows_dev, hist_rows_dev, rr, ncols,
+                                                                              partials, counters, packed_dev);
     HEPMC_LAUNCH_CHECK();
     return 0;
 }
@@ -618,6 +633,7 @@ int hepmc_vegas_integrate(const hepmc_density_t* dens, double* grid_dev, int ndi
     double* scratch = packed + HEPMC_N_SLOTS * (3 + cols);
     int64_t begin[HEPMC_N_SLOTS + 1];
     slot_ranges(nc, begin);
+    HEPMC_CUDA(cudaMemsetAsync(scratch + (size_t)HEPMC_N_SLOTS * kSlotGroups * (3 + cols), 0, 256, as_stream(stream)));
     for (int j = 0; j < iterations; ++j) {
         int e = hepmc_vegas_sample(dens, grid_dev, ndim, divisions, n, 0, chunk, seed, stream_id0 + (uint32_t)j, rng_mode,
                                    nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats_p, hist_p, stream);

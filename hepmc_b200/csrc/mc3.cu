@@ -18,6 +18,7 @@ struct Mc3Args {
     int local_kind;       // 0 = Gaussian random walk (scale = sqrt(diag cov)), 1 = HMC (scale = sqrt(mass)),
                           // 2 = UniformLocal (scale = delta, box [prop_lo, prop_hi])
     const int64_t* sel_replay;  // (C, T-1): 0 = IS update, 1 = local update
+    unsigned long long* local_steps;   // optional: number of local updates taken, summed over the chains
 };
 
 __device__ __forceinline__ double mixture_pdf(const double* tab, int nch, int ndim, const double* x) {
@@ -75,8 +76,7 @@ __global__ void __launch_bounds__(128) mc3_kernel(const __grid_constant__ Dens d
     const PhiloxKey key = philox_expand(a.seed);
     constexpr int NCALL = (NDIM + 1) / 2;
     constexpr uint32_t CPS = NCALL + 2;  // [selector + channel pick | NCALL sample draws | accept uniform]
-    const double half_eps = a.step_size / 2;
-    int64_t acc = 0;
+    int64_t acc = 0, nloc = 0;
     if (active) {
         const uint64_t g = (uint64_t)(a.first_chain + c);
         double x[NDIM];
@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(128) mc3_kernel(const __grid_constant__ Dens d
                 u_ch = u52(r.z, r.w);
             }
             double cand[NDIM], cpdf, prob;
+            nloc += is_step ? 0 : 1;
             if (is_step) {
                 // ---- importance-sampling Metropolis-Hastings: candidate ~ mixture (independent of x)
                 if (replay) {
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(128) mc3_kernel(const __grid_constant__ Dens d
                 prob = cpdf / pdf;  // metropolis.py:50 (the reference treats the proposal as symmetric)
             } else {
                 // ---- local HMC (hmc.py:54-88, simulation.py:34-42)
-                double p0[NDIM], p[NDIM], grad[NDIM];
+                double p0[NDIM], p[NDIM];
                 if (replay) {
 #pragma unroll
                     for (int d = 0; d < NDIM; ++d) p0[d] = draw[d];
@@ -188,16 +189,7 @@ __global__ void __launch_bounds__(128) mc3_kernel(const __grid_constant__ Dens d
                 }
 #pragma unroll
                 for (int d = 0; d < NDIM; ++d) { cand[d] = x[d]; p[d] = p0[d]; }
-                gradient(cand, grad);
-                for (int s = 0; s < a.steps; ++s) {
-#pragma unroll
-                    for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
-#pragma unroll
-                    for (int d = 0; d < NDIM; ++d) cand[d] += a.step_size * (pdist.c[d] * (p[d] - pdist.a[d]));
-                    gradient(cand, grad);
-#pragma unroll
-                    for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
-                }
+                leapfrog_steps<NDIM>(gradient, pdist, cand, p, a.step_size, a.steps);
                 cpdf = density_pdf_n<NDIM>(dens, cand);
                 prob = cpdf * density_pdf_n<NDIM>(pdist, p) / pdf / density_pdf_n<NDIM>(pdist, p0);
                 if (isnan(prob)) prob = 0.0;  // hmc.py:58-59
@@ -227,6 +219,10 @@ __global__ void __launch_bounds__(128) mc3_kernel(const __grid_constant__ Dens d
         }
     }
     finish_counts(a, active && writer, c, acc);
+    if (m.local_steps) {
+        const int64_t tot = warp_sum_i64((active && writer) ? nloc : 0);
+        if ((threadIdx.x & 31) == 0 && tot) atomicAdd(m.local_steps, (unsigned long long)tot);
+    }
 }
 
 }  // namespace hepmc
@@ -235,12 +231,12 @@ using namespace hepmc;
 
 extern "C" int hepmc_mc3_chains(const hepmc_density_t* dens, const double* channel_table_dev, int n_channels, double beta,
                                 int local_kind, const double* local_scale_host, double step_size, int steps,
-                                const hepmc_elm_t* elm, int precision, const double* x0_dev,
+                                const hepmc_elm_t* elm, int precision, int coop_flag, const double* x0_dev,
                                 int64_t n_chains, int64_t first_chain, int64_t sample_size, int64_t thin,
                                 uint64_t seed, uint32_t stream_id,
                                 const int64_t* sel_replay_dev, const double* draw_replay_dev, const double* u_replay_dev,
                                 double* chain_dev, double* last_dev, int64_t* accepted_dev, int64_t* total_accepted_dev,
-                                void* stream) {
+                                int64_t* local_steps_dev, void* stream) {
     HEPMC_REQUIRE(dens && channel_table_dev && x0_dev, HEPMC_E_ARG, "hepmc_mc3_chains: NULL dens/table/x0");
     HEPMC_REQUIRE(dens->kind >= HEPMC_CAMEL && dens->kind <= HEPMC_UNIFORM, HEPMC_E_ARG,
                   "hepmc_mc3_chains: target must be a built-in density");
@@ -291,14 +287,15 @@ extern "C" int hepmc_mc3_chains(const hepmc_density_t* dens, const double* chann
                       "Banana.pot_gradient exists for ndim == 2 only");
     }
     if (n_chains == 0) return 0;
-    Mc3Args m{channel_table_dev, n_channels, beta, local_kind, sel_replay_dev};
+    Mc3Args m{channel_table_dev, n_channels, beta, local_kind, sel_replay_dev,
+              reinterpret_cast<unsigned long long*>(local_steps_dev)};
     int dev = 0, maxs = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&maxs, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const size_t esz = precision == 0 ? 8 : 4;
     size_t smem = (size_t)n_channels * kMcRow * 8 + (el.mode == HEPMC_GRAD_EXACT ? 0 : (size_t)el.nodes * elm_row(nd) * esz);
     HEPMC_REQUIRE(smem <= (size_t)maxs, HEPMC_E_UNSUPPORTED, "hepmc_mc3_chains: tables need %zu bytes of shared memory", smem);
-    const bool coop = el.mode != HEPMC_GRAD_EXACT && n_chains <= coop_max_chains(el.nodes);
+    const bool coop = use_coop(coop_flag, el.mode != HEPMC_GRAD_EXACT, n_chains, el.nodes);
     const unsigned blocks = coop ? (unsigned)n_chains : (unsigned)((n_chains + 127) / 128);
     cudaStream_t st = as_stream(stream);
 #define MC3_LAUNCH(ND, TT, CO)                                                                                  \

@@ -36,6 +36,9 @@ class HamiltonianUpdate(MetropolisUpdate):
         self.p_dist = p_dist
         self.target_density = target_density
         self.precision = precision
+        # hmc.py:47-52.  The fused ensemble kernel integrates with HamiltonLeapfrog's loop; any OTHER simulator
+        # (a `simulate` callable or a custom `sim_class`, e.g. a different splitting) is honoured by the
+        # per-step device path: it is called as simulate(q, p) on (C, ndim) CUDA tensors once per transition.
         if simulate is None:
             self.simulate = sim_class(target_density.pot_gradient, p_dist.pot_gradient, step_size, steps)
         else:
@@ -63,12 +66,25 @@ class HamiltonianUpdate(MetropolisUpdate):
     def _run_ensemble(self, x0, sample_size, thin, store_chain, first_chain, replay):
         from ..surrogate.extreme_learning import SurrogateGradient
         tgt = self.target_density
-        user_target = not isinstance(tgt, BuiltinDensity) or "pdf" in vars(tgt)
+        from ..core.density import as_builtin
+        user_target = as_builtin(tgt) is None or (
+            not type(tgt).__module__.startswith("hepmc_b200.") and
+            type(tgt).pot_gradient is not BuiltinDensity.pot_gradient)     # class-level override of the gradient
         if not isinstance(self.p_dist, Gaussian):
             raise TypeError("the momentum distribution must be densities.Gaussian")
         if np.any(self.p_dist.mean != 0):
             raise TypeError("the momentum distribution must have zero mean")
         mass = self.p_dist._diag()
+        custom_sim = type(self.simulate) is not HamiltonLeapfrog
+        if custom_sim:
+            # a user-supplied simulator cannot run inside the chain kernel: per-step device path, the
+            # simulator receives and returns (C, ndim) CUDA tensors (replay tapes are not available here)
+            if replay is not None:
+                raise TypeError("replay tapes drive the fused kernel; they are not available with a custom simulator")
+            if not callable(self.simulate):
+                raise TypeError("simulate must be callable as simulate(q, p) -> (q_next, p_next)")
+            return ensemble.run_hmc_generic(tgt.pdf, None, x0, mass, None, None, sample_size, thin, store_chain,
+                                            first_chain, simulate=self.simulate)
         if user_target:
             # user-defined target: per-step launches, the user's pdf / pot_gradient run on (C, ndim) CUDA tensors
             if replay is not None or not (callable(getattr(tgt, "pdf", None)) and callable(getattr(tgt, "pot_gradient", None))):
@@ -77,7 +93,10 @@ class HamiltonianUpdate(MetropolisUpdate):
             return ensemble.run_hmc_generic(tgt.pdf, tgt.pot_gradient, x0, mass, float(self.step_size), int(self.steps),
                                             sample_size, thin, store_chain, first_chain)
         grad = vars(tgt).get("pot_gradient", None)
-        grad = getattr(grad, "fn", grad)            # unwrap util.count_calls
+        counted = grad if hasattr(grad, "count") and hasattr(grad, "fn") else None
+        grad = getattr(grad, "fn", grad)            # unwrap util.count_calls (counted below)
+        if getattr(grad, "__self__", None) is tgt and getattr(grad, "__func__", None) is type(tgt).pot_gradient:
+            grad = None                             # the density's own gradient behind the counter
         elm_blk, keep = None, None
         if grad is not None:
             if not isinstance(grad, SurrogateGradient):
@@ -101,7 +120,12 @@ class HamiltonianUpdate(MetropolisUpdate):
                                   "cancellation." % (kappa, TC_CANCELLATION_LIMIT), RuntimeWarning, stacklevel=3)
             prec = self._tc_mode
         out = ensemble.run_hmc(tgt._block(), elm_blk, prec, x0, mass, self.step_size, self.steps,
-                               sample_size, thin, store_chain, first_chain, None, replay)
+                               sample_size, thin, store_chain, first_chain, None, replay,
+                               getattr(self, "_total_chains", None))
+        if counted is not None:
+            # every transition evaluates the gradient steps + 1 times (simulation.py:34-42), one row per
+            # call in the reference: count += chains * transitions * (steps + 1)
+            counted.count += x0.shape[0] * (sample_size - 1) * (int(self.steps) + 1)
         del keep
         return out
 

@@ -181,8 +181,10 @@ int hepmc_vegas_update_grid(const double* slot_stats_dev, const double* slot_his
 /* The slot reduction of one VEGAS iteration in one call: chunk partial rows (stats (n_chunks,3), hist
  * (n_chunks, ncols)) -> PACKED slot rows packed_dev (n_out, 3 + ncols) = [count, mean, M2, hist...], the
  * layout that is all-gathered between GPUs (vegas.py:108-111).  Two levels with fixed row groups and a
- * fixed combine order: bit-identical for any partition of the slots over GPUs.  scratch_dev:
- * hepmc_reduce_slots_scratch_bytes(n_out, ncols) bytes of device memory. */
+ * fixed combine order (one launch: the last level-1 CTA of a slot runs its level 2): bit-identical for
+ * any partition of the slots over GPUs.  scratch_dev: hepmc_reduce_slots_scratch_bytes(n_out, ncols)
+ * bytes of device memory whose LAST 256 bytes (arrival counters) are zero before the first call; the
+ * kernel leaves them zero, so the same scratch serves every iteration. */
 int64_t hepmc_reduce_slots_scratch_bytes(int n_out, int ncols);
 int hepmc_reduce_slots(const double* stats_rows_dev, const double* hist_rows_dev, const int64_t* row_begin_host,
                        int n_out, int ncols, double* packed_dev, void* scratch_dev, void* stream);
@@ -308,14 +310,31 @@ typedef struct hepmc_elm {
  * GEMMs: every term of the gradient sum carries ~2^-11 relative error, fine while the trained
  * weights cancel by less than ~1e3; 3 = exponent GEMM on the tensor cores (3xTF32), contraction
  * with the output weights in FP32 on the FMA pipe (float32-level accuracy for any weights).
- * The Metropolis test always uses the float64 target pdf, so 1, 2 and 3 stay exact samplers. */
-int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int precision,
+ * The Metropolis test always uses the float64 target pdf, so 1, 2 and 3 stay exact samplers.
+ * coop (surrogate gradients, precision 0/1): 1 = one CTA per chain with the node sum of every gradient
+ * split over its threads (small ensembles), 0 = one chain per thread, -1 = decide from n_chains of THIS
+ * call.  The two layouts add the node terms in different orders (last-bit differences), so a caller
+ * that shards one ensemble over several calls or GPUs passes 0 or 1 to keep the chains independent of
+ * the sharding. */
+int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int precision, int coop,
                      const double* x0_dev, const double* mass_host, double step_size, int steps,
                      int64_t n_chains, int64_t first_chain, int64_t sample_size, int64_t thin,
                      uint64_t seed, uint32_t stream_id,
                      const double* p_replay_dev, const double* u_replay_dev,
                      double* chain_dev, double* last_dev, int64_t* accepted_dev,
                      int64_t* total_accepted_dev, void* stream);
+
+/* HamiltonLeapfrog.__call__ (hamiltonian/simulation.py:26-46), batched: n independent states (q, p),
+ * q_dev / p_dev (n, ndim), -> the states after `steps` leapfrog steps of size step_size:
+ *   g = dU(q);  steps x { p -= eps/2 g;  q += eps (p / mass);  g = dU(q);  p -= eps/2 g }
+ * (half steps not merged, steps + 1 gradient evaluations, exactly the loop hepmc_hmc_chains runs).
+ * dU = the density's pot_gradient or the ELM surrogate (elm non-NULL; precision 0 / 1; coop as in
+ * hepmc_hmc_chains); kinetic term = Gaussian(0, diag mass_host).pot_gradient (gaussian.py:45-47).
+ * Outputs may alias the inputs.  Non-finite results are returned as such (the reference returns
+ * (None, None) on a NumPy RuntimeWarning; the host mirror maps all-non-finite states to that). */
+int hepmc_leapfrog(const hepmc_density_t* dens, const hepmc_elm_t* elm, int precision, int coop,
+                   const double* mass_host, double step_size, int steps, int64_t n,
+                   const double* q_dev, const double* p_dev, double* q_out_dev, double* p_out_dev, void* stream);
 
 /* ---- (MC)^3 mixing chains ("next" row 3): replaces MixingMarkovUpdate.next_state
  * (core/markov/base.py:139-179) over [DefaultMetropolis(target, MultiChannel) , local update],
@@ -330,15 +349,18 @@ int hepmc_hmc_chains(const hepmc_density_t* dens, const hepmc_elm_t* elm, int pr
  * channel_table_dev as in hepmc_multichannel_sample.  Replay tapes (all three or none):
  * sel_replay_dev (C, T-1) int64 (0 = IS update, 1 = local), draw_replay_dev (C, T-1, ndim) = the
  * candidate (IS) / standard normals (random walk) / momentum (HMC) / proposal uniform (UniformLocal),
- * u_replay_dev (C, T-1).  Outputs as hepmc_rwm_chains. */
+ * u_replay_dev (C, T-1).  Outputs as hepmc_rwm_chains; local_steps_dev (optional, one int64, zeroed by
+ * the caller) receives the number of local updates taken over all chains (the evaluation counter of
+ * util.count_calls: every local HMC update costs steps + 1 gradient evaluations).  coop as in
+ * hepmc_hmc_chains. */
 int hepmc_mc3_chains(const hepmc_density_t* dens, const double* channel_table_dev, int n_channels, double beta,
                      int local_kind, const double* local_scale_host, double step_size, int steps,
-                     const hepmc_elm_t* elm, int precision, const double* x0_dev,
+                     const hepmc_elm_t* elm, int precision, int coop, const double* x0_dev,
                      int64_t n_chains, int64_t first_chain, int64_t sample_size, int64_t thin,
                      uint64_t seed, uint32_t stream_id,
                      const int64_t* sel_replay_dev, const double* draw_replay_dev, const double* u_replay_dev,
                      double* chain_dev, double* last_dev, int64_t* accepted_dev, int64_t* total_accepted_dev,
-                     void* stream);
+                     int64_t* local_steps_dev, void* stream);
 
 /* ---- ELM surrogate: replaces FunctionBasis.eval (extreme_learning.py:18-29),
  * RadialBasis.output_matrix/eval_gradient (:190-207,222-230), AdditiveBasis.* (:120-146) */

@@ -462,6 +462,51 @@ def gen_elm_and_hmc(h):
     save("hmc", **hout)
 
 
+def gen_leapfrog(h):
+    """HamiltonLeapfrog.__call__ (hamiltonian/simulation.py:26-46) on its own: one state per call, as
+    the reference uses it; exact camel gradient, ELM surrogate gradient (the weights of elm.npz),
+    banana.  Inputs and outputs only -- the call draws nothing."""
+    from hepmc.hamiltonian.simulation import HamiltonLeapfrog
+    from hepmc.surrogate import extreme_learning as el
+    out = {}
+    rs = np.random.RandomState(SEED + 7)
+    ndim = 8
+    elm = dict(np.load(os.path.join(OUT, "elm.npz")))
+
+    def run(tag, pot_gradient, kin_gradient, eps, steps, q0s, p0s):
+        sim = HamiltonLeapfrog(pot_gradient, kin_gradient, eps, steps)
+        qs, ps = [], []
+        for q0, p0 in zip(q0s, p0s):
+            q, p = sim(q0, p0)
+            qs.append(np.array(q, dtype=np.float64))
+            ps.append(np.array(p, dtype=np.float64))
+        out[tag + "_q0"], out[tag + "_p0"] = np.stack(q0s), np.stack(p0s)
+        out[tag + "_q"], out[tag + "_p"] = np.stack(qs), np.stack(ps)
+        out[tag + "_params"] = np.array([steps, eps])
+
+    n = 24
+    q0s = np.where(rs.randint(0, 2, (n, 1)) == 0, 1 / 3, 2 / 3) + 0.06 * rs.standard_normal((n, ndim))
+    # (a) exact camel gradient, unit mass: the pair HamiltonianUpdate builds (hmc.py:47-50)
+    camel = h.densities.Camel(ndim)
+    run("exact", camel.pot_gradient, h.densities.Gaussian(ndim).pot_gradient, 0.02, 20, q0s, rs.standard_normal((n, ndim)))
+    out["exact_mass"] = np.ones(ndim)
+    # (b) ELM surrogate gradient, mass 10 (interfaces/mc3_hmc_el.py:32-40 wiring)
+    basis = el.GaussianBasis(ndim)
+    grad = lambda xs: basis.eval_gradient((elm["g100_centers"], elm["g100_widths"], None), elm["g100_bias"],
+                                          elm["g100_weights"], xs)
+    run("elm", grad, h.densities.Gaussian(ndim, cov=10.).pot_gradient, 0.1, 10, q0s,
+        np.sqrt(10.) * rs.standard_normal((n, ndim)))
+    out["elm_mass"] = np.full(ndim, 10.)
+    # (c) banana 2-D (examples/hmc_banana.py), zero steps included (identity)
+    qb = np.stack([[0., 10.], [2., 6.], [-3., 4.], [0.5, 9.5]])
+    run("banana", h.densities.Banana(2).pot_gradient, h.densities.Gaussian(2).pot_gradient, 0.1, 10, qb,
+        rs.standard_normal((4, 2)))
+    out["banana_mass"] = np.ones(2)
+    run("banana0", h.densities.Banana(2).pot_gradient, h.densities.Gaussian(2).pot_gradient, 0.1, 0, qb,
+        rs.standard_normal((4, 2)))
+    save("leapfrog", **out)
+
+
 def gen_ks_reference():
     """Regenerate testsuit/reference_camel-1M.2d.npy (missing blob) as its 15x15
     histogram + edges -- what testsuit/testing/Analyse.py:37-38 makes of it --
@@ -768,6 +813,7 @@ def main():
     gen_rambo_diet(h)
     gen_stats(h)
     gen_stratified(h)
+    gen_leapfrog(h)
     gen_ks_reference()
 
 

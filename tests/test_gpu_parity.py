@@ -748,6 +748,181 @@ def test_hmc_replay(tag):
     assert s.target is target
 
 
+# ------------------------------------------------------------------ leapfrog / single transitions (a19, a20)
+def _leapfrog_pair(tag):
+    """(pot_gradient, kin_gradient) built like HamiltonianUpdate builds them (hmc.py:47-50)."""
+    g = G("leapfrog")
+    if tag.startswith("banana"):
+        target, ndim = H.densities.Banana(2), 2
+    else:
+        target, ndim = H.densities.Camel(8), 8
+    if tag == "elm":
+        e, params, bias, w = _elm("g100")
+        H.surrogate.attach_surrogate_gradient(target, H.surrogate.GaussianBasis(8), params, bias, w)
+    mass = g[tag.rstrip("0") + "_mass"]
+    return g, target.pot_gradient, H.densities.Gaussian(ndim, cov=float(mass[0])).pot_gradient
+
+
+@pytest.mark.parametrize("tag", ["exact", "elm", "banana", "banana0"])
+def test_leapfrog_replay(tag):
+    """HamiltonLeapfrog.__call__ (simulation.py:26-46) against the reference's own outputs: the callable
+    alone, batched and one state at a time, kernel path and user-callable path."""
+    g, pot_grad, kin_grad = _leapfrog_pair(tag)
+    steps, eps = g[tag + "_params"]
+    sim = H.hamiltonian.HamiltonLeapfrog(pot_grad, kin_grad, float(eps), int(steps))
+    q0, p0 = g[tag + "_q0"], g[tag + "_p0"]
+    # the surrogate's weights are O(1e6) and cancel by ~1e3 in the gradient sum: its tolerance is relative
+    # to that conditioning (the float64 sum order differs from NumPy's), everything else is at 1e-12
+    tol = 1e-9 if tag == "elm" else RTOL
+    q, p = sim(q0, p0)                                            # (C, ndim) batch, one kernel
+    assert isinstance(q, np.ndarray) and q.shape == q0.shape
+    assert_close(q, g[tag + "_q"], tol, atol=tol * 1e-2)
+    assert_close(p, g[tag + "_p"], tol, atol=tol)
+    q1, p1 = sim(q0[0], p0[0])                                    # the reference's call: one state, (ndim,) out
+    assert q1.shape == (q0.shape[1],) and np.array_equal(q1, q[0]) and np.array_equal(p1, p[0])
+    qt, pt = sim(torch.as_tensor(q0, device="cuda"), torch.as_tensor(p0, device="cuda"))
+    assert isinstance(qt, torch.Tensor) and np.array_equal(qt.cpu().numpy(), q)
+    # user-supplied gradients (any callables on CUDA tensors): same loop as device tensor operations
+    if tag == "exact":
+        tgt, pd = H.densities.Camel(8), H.densities.Gaussian(8)
+        sim_u = H.hamiltonian.HamiltonLeapfrog(lambda x: tgt.pot_gradient(x), lambda x: pd.pot_gradient(x), float(eps), int(steps))
+        qu, pu = sim_u(q0, p0)
+        assert_close(qu, g[tag + "_q"], RTOL, atol=1e-14)
+        assert_close(pu, g[tag + "_p"], RTOL, atol=1e-12)
+    # leaving the support: the reference returns (None, None) on overflow; non-finite single states do too
+    if tag == "exact":
+        bad = sim(np.full(8, 5.0), np.zeros(8))                   # outside the unit cube: pot_gradient = inf
+        assert bad == (None, None)
+
+
+@pytest.mark.parametrize("tag", ["exact", "elm", "banana"])
+def test_hmc_single_transitions_replay(tag):
+    """Every transition of the reference's HMC chains as its OWN T = 2 run started from the reference's
+    state: separates the arithmetic of one transition (1e-12) from the growth of rounding differences
+    along a trajectory (test_hmc_replay: 1e-8 after 59 transitions)."""
+    g = G("hmc")
+    steps, eps, mass = g[tag + "_params"]
+    chain = g[tag + "_chain"]
+    S, T, ndim = chain.shape
+    target = H.densities.Banana(2) if tag == "banana" else H.densities.Camel(ndim)
+    if tag == "elm":
+        e, params, bias, w = _elm("g100")
+        H.surrogate.attach_surrogate_gradient(target, H.surrogate.GaussianBasis(ndim), params, bias, w)
+    upd = H.hamiltonian.HamiltonianUpdate(target, H.densities.Gaussian(ndim, cov=mass), int(steps), float(eps))
+    starts = chain[:, :-1].reshape(-1, ndim)
+    expect = chain[:, 1:].reshape(-1, ndim)
+    s = upd.sample(2, starts, replay=(g[tag + "_p"].reshape(-1, 1, ndim), _fill(g[tag + "_u"]).reshape(-1, 1)))
+    moved = np.any(expect != starts, axis=1)
+    assert np.array_equal(s.accepted, moved.astype(np.int64))     # every accept/reject decision
+    assert np.array_equal(s.data[:, 0], starts)
+    tol = 1e-9 if tag == "elm" else RTOL                          # see test_leapfrog_replay
+    assert_close(s.data[:, 1], expect, tol, atol=tol * 1e-2)
+    assert moved.sum() >= 100
+
+
+@pytest.mark.parametrize("tag", ["hmc", "rwm", "unif"])
+def test_mixing_single_transitions_replay(tag):
+    """The three (MC)^3 variants, every transition of the reference chains on its own (T = 2) at 1e-12."""
+    g = G("mixing")
+    target, channels, is_upd, local = _mixing_setup(tag, g["weights"])
+    mix = H.MixingMarkovUpdate(2, [is_upd, local], [0.4, 0.6])
+    chain = g[tag + "_chain"]
+    if chain.ndim == 2:
+        chain = chain[None]
+    S, T, ndim = chain.shape
+    starts = chain[:, :-1].reshape(-1, ndim)
+    expect = chain[:, 1:].reshape(-1, ndim)
+    sel = np.asarray(g[tag + "_sel"]).reshape(-1, 1)
+    draw = np.asarray(g[tag + "_draw"]).reshape(-1, 1, ndim)
+    u = _fill(np.asarray(g[tag + "_u"])).reshape(-1, 1)
+    s = mix.sample(2, starts, replay=(sel, draw, u))
+    moved = np.any(expect != starts, axis=1)
+    assert np.array_equal(s.accepted, moved.astype(np.int64))
+    assert_close(s.data[:, 1], expect, RTOL, atol=1e-14)
+
+
+def test_hmc_custom_simulator_is_honoured():
+    """hmc.py:25-27: `simulate=` / `sim_class=` other than HamiltonLeapfrog run through the per-step device
+    path and ARE called (round 1 accepted and ignored them)."""
+    calls = []
+
+    class Half(H.hamiltonian.HamiltonLeapfrog):              # a user's simulator class: half the step count
+        def __call__(self, q, p):
+            calls.append(tuple(q.shape))
+            inner = H.hamiltonian.HamiltonLeapfrog(self.pot_gradient, self.kin_gradient, self.step_size, self.steps // 2)
+            return inner(q, p)
+
+    H.seed(31)
+    tgt = H.densities.Camel(2)
+    upd = H.hamiltonian.HamiltonianUpdate(tgt, H.densities.Gaussian(2), 10, 0.02, sim_class=Half)
+    assert isinstance(upd.simulate, Half) and upd.steps == 10
+    C, T = 512, 40
+    s = upd.sample(T, np.tile([0.3, 0.35], (C, 1)), store_chain=False)
+    assert len(calls) == T - 1 and calls[0] == (C, 2)
+    assert 0.5 < s.accepted.mean() / T <= 1.0 and np.all((s.data > 0) & (s.data < 1))
+    # the same through simulate=: a plain function of (q, p)
+    ref = H.hamiltonian.HamiltonLeapfrog(tgt.pot_gradient, H.densities.Gaussian(2).pot_gradient, 0.02, 10)
+    H.seed(31)
+    upd2 = H.hamiltonian.HamiltonianUpdate(tgt, H.densities.Gaussian(2), 10, 0.02, simulate=lambda q, p: ref(q, p))
+    s2 = upd2.sample(T, np.tile([0.3, 0.35], (C, 1)), store_chain=False)
+    # ... which, with HamiltonLeapfrog's own loop inside, reproduces the generic path of the default simulator
+    # step for step (same draws, same arithmetic up to the kernel's fused operations)
+    assert 0.5 < s2.accepted.mean() / T <= 1.0
+    with pytest.raises(TypeError):
+        upd2.sample(3, np.tile([0.3, 0.35], (2, 1)), replay=(np.zeros((2, 2, 2)), np.zeros((2, 2))))
+
+
+def test_count_calls_counts_in_kernel_evaluations():
+    """util.count_calls (helper.py:106-122; interfaces/mc3_hmc_el.py:35): fused kernels evaluate the
+    gradient in-kernel, the counter advances by rows x calls all the same."""
+    e, params, bias, w = _elm("g100")
+    tgt = H.densities.Camel(8)
+    H.surrogate.attach_surrogate_gradient(tgt, H.surrogate.GaussianBasis(8), params, bias, w)
+    H.util.count_calls(tgt, "pot_gradient")
+    upd = H.hamiltonian.HamiltonianUpdate(tgt, H.densities.Gaussian(8, cov=10.), 10, 0.1)
+    C, T = 7, 12
+    upd.sample(T, np.full((C, 8), 1 / 3))
+    assert tgt.pot_gradient.count == C * (T - 1) * 11            # steps + 1 evaluations per transition
+    tgt.pot_gradient(np.full((5, 8), 0.4))                        # a direct call still counts its rows
+    assert tgt.pot_gradient.count == C * (T - 1) * 11 + 5
+    # exact gradient behind the counter, and the mixing kernel (counts the local HMC updates it took)
+    t2 = H.densities.Camel(2)
+    H.util.count_calls(t2, "pot_gradient")
+    channels = H.MultiChannel([H.densities.Gaussian(2, mu=1 / 3, scale=0.1), H.densities.Gaussian(2, mu=2 / 3, scale=0.1),
+                               H.densities.Uniform(2)], np.array([0.4, 0.4, 0.2]))
+    local = H.hamiltonian.HamiltonianUpdate(t2, H.densities.Gaussian(2), 10, 0.02)
+    local.sample(5, np.tile([0.3, 0.35], (3, 1)))
+    assert t2.pot_gradient.count == 3 * 4 * 11
+    before = t2.pot_gradient.count
+    mix = H.MixingMarkovUpdate(2, [H.DefaultMetropolis(2, t2, channels), local], [0.5, 0.5])
+    C, T = 2000, 21
+    mix.sample(T, np.tile([0.3, 0.35], (C, 1)), store_chain=False)
+    n_local = (t2.pot_gradient.count - before) / 11
+    assert n_local == int(n_local) and abs(n_local / (C * (T - 1)) - 0.5) < 0.02
+
+
+def test_surrogate_hmc_does_not_depend_on_the_sharding():
+    """the cooperative / thread-per-chain choice follows the GLOBAL ensemble size
+    (total_chains, or the sum over the process group), so a chain is bit-identical whether it runs in
+    one call or in a shard."""
+    e, params, bias, w = _elm("g100")
+    rs = np.random.default_rng(5)
+    x0 = 1 / 3 + 0.05 * rs.standard_normal((3000, 8))             # > 1024: thread-per-chain layout
+
+    def run(lo, hi, total):
+        H.seed(777)
+        tgt = H.densities.Camel(8)
+        H.surrogate.attach_surrogate_gradient(tgt, H.surrogate.GaussianBasis(8), params, bias, w)
+        upd = H.hamiltonian.HamiltonianUpdate(tgt, H.densities.Gaussian(8, cov=10.), 10, 0.1)
+        return upd.sample(12, x0[lo:hi], first_chain=lo, total_chains=total)
+    whole = run(0, 3000, None)
+    shard = run(1500, 1500 + 700, 3000)                          # 700 chains alone would pick the cooperative kernel
+    assert np.array_equal(shard.data, whole.data[1500:2200]) and np.array_equal(shard.accepted, whole.accepted[1500:2200])
+    small = run(0, 600, 600)                                     # a small ensemble, sharded 2 x 300
+    a, b = run(0, 300, 600), run(300, 600, 600)
+    assert np.array_equal(np.concatenate([a.data, b.data]), small.data)
+
+
 def test_hmc_native_statistics_and_precisions():
     """Camel-8D, ELM surrogate gradient, float64 vs float32 surrogate arithmetic: both are
     exact samplers (MH test on the float64 pdf); moments agree with the target."""

@@ -165,6 +165,45 @@ def test_hmc(tag):
     assert_close(chain, g[tag + "_chain"], 1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("tag", ["exact", "elm", "banana", "banana0"])
+def test_leapfrog(tag):
+    """O.leapfrog against the reference's HamiltonLeapfrog.__call__ (simulation.py:26-46), bit for bit."""
+    g = G("leapfrog")
+    e = G("elm")
+    steps, eps = g[tag + "_params"]
+    base = tag.rstrip("0")
+    if base == "exact":
+        grad = O.camel_pot_gradient
+    elif base == "elm":
+        grad = lambda q: O.elm_gauss_eval_gradient(q, e["g100_centers"], e["g100_widths"], e["g100_weights"])
+    else:
+        grad = O.banana_pot_gradient
+    kin = lambda p: O.gaussian_pot_gradient(p, 0.0, g[base + "_mass"])
+    q, p = O.leapfrog(grad, kin, g[tag + "_q0"], g[tag + "_p0"], eps, int(steps))
+    assert np.array_equal(q, g[tag + "_q"]) and np.array_equal(p, g[tag + "_p"])
+
+
+@pytest.mark.parametrize("tag", ["exact", "elm", "banana"])
+def test_hmc_single_transitions(tag):
+    """Every transition of the reference chains on its own (T = 2): the oracle is bit-exact per transition."""
+    g = G("hmc")
+    e = G("elm")
+    steps, eps, mass = g[tag + "_params"]
+    if tag == "exact":
+        pdf, grad = O.camel_pdf, O.camel_pot_gradient
+    elif tag == "elm":
+        pdf = O.camel_pdf
+        grad = lambda q: O.elm_gauss_eval_gradient(q, e["g100_centers"], e["g100_widths"], e["g100_weights"])
+    else:
+        pdf, grad = O.banana_pdf, O.banana_pot_gradient
+    chain = g[tag + "_chain"]
+    nd = chain.shape[2]
+    starts, expect = chain[:, :-1].reshape(-1, nd), chain[:, 1:].reshape(-1, nd)
+    c2, acc = O.hmc_chains(pdf, grad, starts, g[tag + "_p"].reshape(-1, 1, nd), _fill(g[tag + "_u"]).reshape(-1, 1),
+                           mass, eps, int(steps))
+    assert np.array_equal(c2[:, 1], expect)
+
+
 def _mc_channels(g):
     return [("gauss", 1 / 3, 0.01), ("gauss", g["chan_mu1"], g["chan_cov1"]), ("uniform", 0., 1.)]
 
