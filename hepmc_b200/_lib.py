@@ -72,7 +72,7 @@ SIGNATURES = {
     "hepmc_multichannel_sample": (_int, [_dens_p, _vp, _int, _int, _i64, _i64, _i64, _u64, _u32,
                                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hepmc_multichannel_accumulate": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _vp, _vp, _vp]),
-    "hepmc_rambo_map": (_int, [_int, _dbl, _i64, _i64, _u64, _u32, _vp, _vp, _vp]),
+    "hepmc_rambo_map": (_int, [_int, _dbl, _i64, _i64, _u64, _u32, _int, _vp, _vp, _vp]),
     "hepmc_rambo_diet_map": (_int, [_int, _dbl, _i64, _i64, _u64, _u32, _vp, _vp, _vp]),
     "hepmc_rambo_diet_inverse": (_int, [_int, _dbl, _i64, _vp, _vp, _vp]),
     "hepmc_accept_flags": (_int, [_vp, _vp, _dbl, _dbl, _i64, _i64, _u64, _u32, _vp, _vp]),

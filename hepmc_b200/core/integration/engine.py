@@ -11,6 +11,7 @@ import torch
 from ... import _lib, rng, parallel
 from ..density import as_builtin
 from ..util import host_function
+from ..util.helper import call_user_function
 
 
 def none_block(ndim):
@@ -36,20 +37,11 @@ def uniform_rvs(n, ndim, stream_id=None):
 def call_integrand(fn, cols):
     """Evaluate a user integrand on the sample columns (CUDA tensors, or host arrays for a
     `host_function`) and return the values as a float64 CUDA tensor."""
-    if isinstance(fn, host_function):
-        vals = fn(*[c.cpu().numpy() for c in cols])
-    else:
-        if len(cols) > 1 and cols[0].stride(0) != 1:
-            # columns of a row-major (N, ndim) block: one transposing copy, then the integrand's
-            # elementwise ops run on contiguous arrays (several times faster than on stride-ndim views)
-            cols = list(torch.stack(cols, dim=0).unbind(0))
-        try:
-            vals = fn(*cols)
-        except TypeError as exc:
-            raise TypeError(
-                "integrand failed on CUDA tensors (%s). Integrands must accept torch CUDA tensors, be a "
-                "built-in hepmc_b200 density, or be wrapped in hepmc_b200.util.host_function to run on the "
-                "host; hepmc_b200 has no CPU fallback of its own." % exc) from exc
+    if not isinstance(fn, host_function) and len(cols) > 1 and cols[0].stride(0) != 1:
+        # columns of a row-major (N, ndim) block: one transposing copy, then the integrand's
+        # elementwise ops run on contiguous arrays (several times faster than on stride-ndim views)
+        cols = list(torch.stack(cols, dim=0).unbind(0))
+    vals = call_user_function(fn, cols, "the integrand")
     n = cols[0].shape[0]
     if isinstance(vals, torch.Tensor):
         vals = vals.to(device=cols[0].device, dtype=torch.float64)

@@ -127,19 +127,14 @@ def run_hmc(blk, elm_blk, precision, x0, mass_diag, step_size, steps, sample_siz
 def _user_values(fn, x, what):
     """fn(x) for x (C, ndim) on the device -> float64 CUDA tensor; fn may answer with a tensor or
     anything np.asarray understands (util.host_function marks NumPy code: it gets a host copy)."""
-    from ..util.helper import host_function
-    if isinstance(fn, host_function):
-        out = fn(x.cpu().numpy())
-    else:
-        try:
-            out = fn(x)
-        except TypeError as exc:
-            raise TypeError("the target's %s failed on a CUDA tensor (%s).  User-defined targets of chain updates "
-                            "must accept torch CUDA tensors of shape (C, ndim), or be wrapped in "
-                            "hepmc_b200.util.host_function." % (what, exc)) from exc
+    from ..util.helper import call_user_function
+    out = call_user_function(fn, [x], "the target's " + what)
     if not isinstance(out, torch.Tensor):
         out = torch.as_tensor(np.asarray(out, dtype=np.float64))
-    return out.to(device=x.device, dtype=torch.float64)
+    out = out.to(device=x.device, dtype=torch.float64)
+    if out.dim() == 0:                       # a constant (`lambda x: 1`, reference tests/test_markov.py:10)
+        out = out.expand(x.shape[0])
+    return out
 
 
 def _step_draws(n_chains, n_uniform, first_chain, stream_id, dev):

@@ -45,7 +45,7 @@ class Rambo(PhaseSpaceMapping):
             raise RuntimeWarning("Unexpected dimension of entries in array.")
         out = torch.empty_like(x_dev)
         if x_dev.shape[0]:
-            _lib.call("hepmc_rambo_map", int(self.nparticles), float(self.e_cm), x_dev.shape[0], 0, 0, 0,
+            _lib.call("hepmc_rambo_map", int(self.nparticles), float(self.e_cm), x_dev.shape[0], 0, 0, 0, 0,
                       _lib.ptr(x_dev), _lib.ptr(out), _lib.stream_ptr())
         return _lib.to_host_like(out, host)
 
@@ -59,7 +59,7 @@ class Rambo(PhaseSpaceMapping):
         sid = rng.next_stream() if stream_id is None else stream_id
         if count:
             _lib.call("hepmc_rambo_map", int(self.nparticles), float(self.e_cm), int(count), int(first_index),
-                      rng.get_seed(), sid, None, _lib.ptr(out), _lib.stream_ptr())
+                      rng.get_seed(), sid, rng.mode_code(), None, _lib.ptr(out), _lib.stream_ptr())
         return out
 
 

@@ -85,6 +85,38 @@ def count_calls(obj, *method_names):
         setattr(obj, name, Counted(getattr(obj, name)))
 
 
+_host_warned = set()
+
+
+def call_user_function(fn, device_args, what):
+    """Call USER code with CUDA tensors; if it turns out to be NumPy code (the reference's integrands and
+    targets are: `lambda x: np.sin(10 * x)`) -- a TypeError / "can't convert cuda tensor" from inside it --
+    call it again with host copies of the arguments, as if it were wrapped in `host_function`, and say so
+    once per function.  This is the user's code running where the user wrote it; the library's own
+    arithmetic (draws, maps, weights, reductions, accept/reject) stays on the device either way."""
+    import warnings
+    if isinstance(fn, host_function):
+        return fn(*[a.cpu().numpy() for a in device_args])
+    if id(fn) in _host_warned:
+        return fn(*[a.cpu().numpy() for a in device_args])
+    try:
+        return fn(*device_args)
+    except (TypeError, RuntimeError) as exc:
+        msg = str(exc)
+        if isinstance(exc, RuntimeError) and "numpy" not in msg.lower() and "cuda" not in msg.lower():
+            raise
+        try:
+            out = fn(*[a.cpu().numpy() for a in device_args])
+        except Exception:
+            raise TypeError("%s failed on CUDA tensors (%s) and on host arrays.  User functions must accept torch CUDA "
+                            "tensors or NumPy arrays." % (what, exc)) from exc
+        _host_warned.add(id(fn))
+        warnings.warn("%s is NumPy code (%s): it is evaluated on the host from device-to-host copies of its "
+                      "arguments; write it with torch operations, or wrap it in hepmc_b200.util.host_function to "
+                      "silence this warning." % (what, type(exc).__name__), RuntimeWarning, stacklevel=3)
+        return out
+
+
 class host_function(object):
     """Marks a user integrand written for NumPy: the integrators hand it host arrays
     (device->host copy of the sample, host->device copy of the values) instead of CUDA

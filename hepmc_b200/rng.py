@@ -14,8 +14,8 @@ _state = {"seed": 1234, "stream": 0}
 #            t = K w: bin = t >> 32, offset = (t mod 2^32 + 1/2) 2^-32; four axes per Philox call
 #   "u52r10": 52-bit uniforms / 64 random bits per (bin, offset) pair, two axes per call
 #   "u32r7":  as u32r10 with Philox4x32-7 (the Crush-resistant minimum of Salmon et al.)
-# The mode applies to PlainMC / VegasMC / StratifiedMC / GridVolumes draws.  RAMBO, the chain
-# kernels and every helper that returns raw uniforms always draw 52-bit uniforms with 10 rounds.
+# The mode applies to PlainMC / VegasMC / StratifiedMC / GridVolumes draws and to phase_space.Rambo.generate.
+# The chain kernels and every helper that returns raw uniforms always draw 52-bit uniforms with 10 rounds.
 MODES = {"u52r10": 0, "u32r10": 1, "u32r7": 2}
 DEFAULT_MODE = "u32r10"
 _state["mode"] = DEFAULT_MODE

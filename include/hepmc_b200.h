@@ -101,7 +101,8 @@ int hepmc_fp64_probe(int64_t iters, double* ms_out, double* flops_out, void* str
  *   HEPMC_RNG_U32_R7:            the same with Philox4x32-7 (the smallest round count that
  *                                passes BigCrush in Salmon et al., SC'11; Random123 KATs).
  * Counters are the same in every mode (item index, call index, stream id), so results stay
- * independent of the GPU count.  RAMBO and the chain kernels always use 52-bit uniforms. */
+ * independent of the GPU count.  The modes apply to the integrators and to RAMBO; the chain kernels
+ * (normal proposals, momenta, accept uniforms) always use 52-bit uniforms with 10 rounds. */
 enum hepmc_rng_mode { HEPMC_RNG_U52_R10 = 0, HEPMC_RNG_U32_R10 = 1, HEPMC_RNG_U32_R7 = 2, HEPMC_RNG_MODES = 3 };
 
 /* ---- densities: replaces Density.pdf/pot/pot_gradient/pdf_gradient ---------------- */
@@ -233,9 +234,11 @@ int hepmc_multichannel_accumulate(const double* f_dev, const double* p_dev, cons
 
 /* ---- RAMBO: replaces phase_space.Rambo.map (rambo.py:38-69,162-173) ---------------- */
 /* out_dev (n, 4*nparticles) as [E,px,py,pz] per particle.  Native RNG (point index
- * first_index + i) unless xs_replay_dev (n, 4*nparticles) is given. */
+ * first_index + i; rng_mode as for the integrators: in the 32-bit modes the four uniforms of
+ * particle p are the four words of Philox call p, in HEPMC_RNG_U52_R10 two calls per particle)
+ * unless xs_replay_dev (n, 4*nparticles) is given. */
 int hepmc_rambo_map(int nparticles, double e_cm, int64_t n, int64_t first_index, uint64_t seed,
-                    uint32_t stream_id, const double* xs_replay_dev, double* out_dev, void* stream);
+                    uint32_t stream_id, int rng_mode, const double* xs_replay_dev, double* out_dev, void* stream);
 /* Rambo.pdf (rambo.py:28-36): the constant 1/Phi_n, computed on the host. */
 double hepmc_rambo_pdf(int nparticles, double e_cm);
 

@@ -10,6 +10,9 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# the reference's own test files are fixtures, run through tests/test_reference_unit_tests.py
+collect_ignore_glob = ["golden/ref_tests/*"]
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
