@@ -145,8 +145,12 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
-            del os.environ["NCCL_DEBUG"]             # keep NCCL's version banner off stdout (one JSON line)
+        # the harness's NCCL_DEBUG stays as it is: NCCL (a C library writing to fd 1) is pointed at stderr
+        # for the life of the process, and the one JSON line goes to the saved stdout
+        global _REAL_STDOUT
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     H.set_outputs("torch")
     dev = torch.device("cuda", local_rank)
@@ -214,6 +218,23 @@ def run_b200(args):
     kernel_ms = float(np.mean(kms))
     fp64_peak = _lib.fp64_probe(1 << 15) / 1e12          # measured DFMA TFLOP/s on this GPU, live
     achieved = FLOP_PER_POINT * n_local / (kernel_ms * 1e-3) / 1e12
+    # the same kernel in the other two draw modes (the headline runs in the library default)
+    mode_ms = {rng.get_mode(): kernel_ms}
+    for mode in ("u52r10", "u32r10", "u32r7"):
+        if mode in mode_ms:
+            continue
+        ts = []
+        for i in range(4):
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            _lib.call("hepmc_vegas_sample", ctypes.byref(blk), _lib.ptr(grid), NDIM, DIVISIONS, n_local, first, chunk,
+                      1234, 2000 + i, rng.MODES[mode], None, None, None, None, None, None, _lib.ptr(sp), _lib.ptr(hp),
+                      _lib.stream_ptr())
+            k1.record()
+            torch.cuda.synchronize()
+            if i >= 1:
+                ts.append(k0.elapsed_time(k1))
+        mode_ms[mode] = float(np.mean(ts))
 
     others = {}
     # the other configs: EVERY rank runs them (the library's reductions look for their peers); the
@@ -242,20 +263,24 @@ def run_b200(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "camel-16D VEGAS, divisions=15, c=3, %.3g points/iteration whole job "
                                "(BASELINE.json configs[2]); keep_samples=False" % n,
+                   "rng_mode": "%s (library default: 32 random bits per axis, Philox4x32-10; hepmc_b200.rng)" % rng.get_mode(),
                    "parallelism": "philox-counter sharding x%d, all-gather of 8 slot partials per iteration" % world,
                    "l2": "no memory-resident input (counter RNG in registers); partial rows are written, never re-read hot",
                    "integral": res.integral, "integral_err": res.integral_err},
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": grid_bytes / steps,
                 "d2h_bytes_per_step": 16, "integral": integral_host},
-        "gpu_launches": 4 * steps,
+        # per iteration: vegas_fast_kernel, reduce_slots_kernel, vegas_update_kernel (+ one NCCL all-gather at N > 1)
+        "gpu_launches": 3 * steps,
         "clocks": sampler.summary(),
         "roofline": {"bound": "fp64_simt", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size from the ncu
-                     # --set full capture (profiles/r01_vegas_sample_kernel_ncu_summary.txt): 70.7 KB + 9.28 MB;
-                     # the 59 MB of partial rows mostly stay in L2 until the reduce kernels read them
-                     "traffic": 9354752 if (n_local == N_POINTS and world == 1) else None,
-                     "kernel": "vegas_sample_kernel", "kernel_ms": kernel_ms, "points_per_launch": n_local,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, read from the
+                     # committed ncu --set full summary of the same command (the 59 MB of partial rows mostly
+                     # stay in L2 until the reduction reads them)
+                     "traffic": _ncu_traffic() if (n_local == N_POINTS and world == 1) else None,
+                     "kernel": "vegas_fast_kernel", "kernel_ms": kernel_ms, "points_per_launch": n_local,
+                     "kernel_ms_by_rng_mode": mode_ms,
+                     "points_per_s_by_rng_mode": {k: n_local / (v * 1e-3) for k, v in mode_ms.items()},
                      "flop_per_point": FLOP_PER_POINT,
                      "peak_source": "live DFMA probe (hepmc_fp64_probe); MEASURED_PEAKS.json has no FP64 entry "
                                     "(hbm_gbs=%s)" % peaks.get("hbm_gbs"),
@@ -265,15 +290,41 @@ def run_b200(args):
                      "hbm_view": {"bound": "hbm", "unit": "GB/s", "peak": peaks.get("hbm_gbs"),
                                   "achieved": nc * (3 + NDIM * DIVISIONS) * 8 / (kernel_ms * 1e-3) / 1e9,
                                   "bytes_per_launch": nc * (3 + NDIM * DIVISIONS) * 8},
-                     "note": "compute-bound FP64 SIMT kernel: 897 thread-instructions per point of which ~420 are the "
-                             "integer Philox4x32-10 rounds and 174 are FP64; issue slots 62 % busy (ncu, profiles/"
-                             "r01_vegas_sample_kernel_ncu_summary.txt)"},
+                     "note": "577 thread-instructions per point (round 1: 897), 165 of them FP64; FP64 pipe 36 %, issue "
+                             "slots 66 %, and the shared-memory data pipe 73 % busy (161 wavefronts per 32 points: grid "
+                             "look-ups and the histogram read-modify-writes) -- the binding resource (ncu, profiles/"
+                             "r02_vegas_fast_kernel_ncu_summary.txt)"},
         "cpu_baseline": cpu,
         "others": others,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, text.encode())
+
+
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the headline kernel from the committed ncu summary."""
+    try:
+        txt = open(os.path.join(ROOT, "profiles", "r02_vegas_fast_kernel_ncu_summary.txt")).read()
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            line = [l for l in txt.splitlines() if key in l][0].split()
+            tot += float(line[1]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[line[2]]
+        return int(tot)
+    except Exception:
+        return None
 
 
 def _best_of(fn, reps=3):
@@ -378,49 +429,83 @@ def other_workloads(H, _lib, torch, fp64_peak, with_cpu, rank=0, world=1):
                                "roofline": {"bound": "hbm", "achieved": 2 * nk * 18 * 8 / t / 1e9, "peak": hbm, "unit": "GB/s",
                                             "frac": 2 * nk * 18 * 8 / t / 1e9 / hbm, "bytes_per_point": 144}}
         del mck
-    # C2: RAMBO 2->4, sqrt(s) = 100 GeV: 2^27 points per launch whole job (16 GiB of output,
-    # larger than L2 at every N)
+    # C2: RAMBO 2->4, sqrt(s) = 100 GeV.  BASELINE.json configs[1]: 1e9 points sharded over 8 GPUs (16 GB of output
+    # per GPU); on fewer GPUs 2^27 points per launch whole job (16 GiB; larger than L2 at every N)
     m = H.phase_space.Rambo(100., 4)
-    nr = 1 << 27
+    nr = 10 ** 9 if world == 8 else 1 << 27
     first, cnt = parallel.item_span(nr, rank, world)
     buf = torch.empty((cnt, 16), dtype=torch.float64, device="cuda")
     t = timed(lambda: m.generate(cnt, first_index=first, out=buf))
     del buf
-    out["rambo"] = {"metric": "RAMBO 2->4 PS-points/s", "value": nr / t, "points": nr,
+    out["rambo"] = {"metric": "RAMBO 2->4 PS-points/s", "value": nr / t, "points": nr, "rng_mode": H.rng.get_mode(),
                     "roofline": {"bound": "hbm", "achieved": nr * 128 / t / 1e9 / world, "peak": hbm, "unit": "GB/s",
                                  "frac": nr * 128 / t / 1e9 / world / hbm, "bytes_per_point": 128, "per": "GPU",
                                  "fp64_tflops_algorithmic": 183 * nr / t / 1e12 / world},
                     "cpu_baseline": cpu.get("rambo")}
-    # C4: banana 2-D RWM: 1e6 chains x 1e3 steps per launch (the 1e4-step config is 10 such launches)
-    C, T = 1_000_000, 1001
+    # C4: banana 2-D RWM: 1e6 chains x 1e4 steps in ONE launch (BASELINE.json configs[3] at full size)
+    C, T = 1_000_000, 10_001
     first, cnt = parallel.item_span(C, rank, world)
     met = H.DefaultMetropolis(2, H.densities.Banana(2), H.proposals.Gaussian(2, cov=10 * np.eye(2)))
     x0 = torch.tensor([[0., 10.]], device="cuda", dtype=torch.float64).repeat(cnt, 1)
-    t = timed(lambda: met.sample(T, x0, store_chain=False, first_chain=first))
+    t = timed(lambda: met.sample(T, x0, store_chain=False, first_chain=first), reps=2)
     out["rwm"] = {"metric": "banana-2D RWM chain-steps/s", "value": C * (T - 1) / t, "chains": C, "steps": T - 1,
                   "roofline": {"bound": "fp64_simt", "achieved": 23 * C * (T - 1) / t / 1e12 / world, "peak": fp64_peak,
                                "unit": "TFLOP/s", "frac": 23 * C * (T - 1) / t / 1e12 / world / fp64_peak,
                                "flop_per_step": 23, "per": "GPU"},
                   "cpu_baseline": cpu.get("rwm")}
-    # C5: camel-8D HMC, ELM Gaussian-basis surrogate gradient, 1e5 chains x 20 leapfrog
-    rs = np.random.default_rng(0)
+    # C5: camel-8D HMC, 1e5 chains x 20 leapfrog, ELM Gaussian-basis surrogate gradient TRAINED by the SURVEY 8(d)
+    # recipe: 4000 points (2000 per mode, N(mu, 0.005 I)), values = UnconstrainedCamel(8).pot(xs), random centres
+    # U[0,1)^(I x 8) and widths U[0.01, 1) (extreme_learning_train's own draw), plain pseudo-inverse (ridge = 0: the
+    # reference, interfaces/mc3_hmc_el.py:24-29) and, as a second line, the ridge = 1e-6 extension.
+    # Rooflines: float64 -> FP64 SIMT by algorithmic flops; f32 / tc32 / tc -> one MUFU.EX2 per (chain, node,
+    # gradient evaluation) against the live MUFU probe (the exponential, not the MMA, bounds this path).
+    mufu_peak = _lib.mufu_probe(1 << 14)
+    rs = np.random.RandomState(1234)
+    xs_train = np.concatenate([1 / 3 + np.sqrt(0.005) * rs.standard_normal((2000, 8)),
+                               2 / 3 + np.sqrt(0.005) * rs.standard_normal((2000, 8))])
+    v_train = H.densities.UnconstrainedCamel(8).pot(xs_train)
+    if isinstance(v_train, torch.Tensor):
+        v_train = v_train.cpu().numpy()
     for nodes in (100, 1024):
-        basis = H.surrogate.GaussianBasis(8)
-        params = (rs.random((nodes, 8)), 0.01 + 0.99 * rs.random(nodes), None)
-        w = 0.01 * rs.standard_normal(nodes)
-        for prec in ("f64", "f32", "tc32", "tc"):
-            tgt = H.densities.Camel(8)
-            H.surrogate.attach_surrogate_gradient(tgt, basis, params, 0.0, w)
-            upd = H.hamiltonian.HamiltonianUpdate(tgt, H.densities.Gaussian(8), 20, 0.01, precision=prec)
-            Ch, Th = 100_000, 3
-            first, cnt = parallel.item_span(Ch, rank, world)
-            x0h = torch.full((cnt, 8), 1 / 3, device="cuda", dtype=torch.float64)
-            t = timed(lambda: upd.sample(Th, x0h, store_chain=False, first_chain=first), reps=2)
-            flop = 21 * (4 * nodes * 8 + 5 * nodes + 4 * 8) + 20 * 64 + 72 + 48
-            out["hmc_elm%d_%s" % (nodes, prec)] = {
-                "metric": "camel-8D HMC+ELM chain-steps/s", "value": Ch * (Th - 1) / t, "nodes": nodes,
-                "achieved_tflops": flop * Ch * (Th - 1) / t / 1e12,
-                "cpu_baseline": cpu.get("hmc_elm%d" % nodes)}
+        for ridge in (0.0, 1e-6):
+            basis = H.surrogate.GaussianBasis(8)
+            np.random.seed(4321 + nodes)
+            H.seed(4321 + nodes)
+            params, bias, w = basis.extreme_learning_train(xs_train, v_train, nodes, ridge=ridge)
+            for prec in ("f64", "f32", "tc32", "tc"):
+                if ridge and prec != "tc":
+                    continue                       # the extension only changes which kernel 'tc' may keep
+                tgt = H.densities.Camel(8)
+                grad = H.surrogate.attach_surrogate_gradient(tgt, basis, params, bias, w)
+                upd = H.hamiltonian.HamiltonianUpdate(tgt, H.densities.Gaussian(8), 20, 0.01, precision=prec)
+                Ch, Th = 100_000, 3
+                first, cnt = parallel.item_span(Ch, rank, world)
+                x0h = torch.full((cnt, 8), 1 / 3, device="cuda", dtype=torch.float64)
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    t = timed(lambda: upd.sample(Th, x0h, store_chain=False, first_chain=first, total_chains=Ch), reps=2)
+                    acc = upd.sample(11, x0h[:20000], store_chain=False, total_chains=Ch).accepted
+                acc = float(acc.double().mean() if isinstance(acc, torch.Tensor) else np.mean(acc)) / 10
+                rate = Ch * (Th - 1) / t
+                flop = 21 * (4 * nodes * 8 + 5 * nodes + 4 * 8) + 20 * 64 + 72 + 48
+                ran = upd.kernel_precision
+                if ran == "f64":
+                    roof = {"bound": "fp64_simt", "achieved": flop * rate / 1e12 / world, "peak": fp64_peak, "unit": "TFLOP/s",
+                            "frac": flop * rate / 1e12 / world / fp64_peak, "flop_per_chain_step": flop, "per": "GPU"}
+                else:
+                    ex = 21 * nodes * rate / world
+                    roof = {"bound": "mufu_ex2", "achieved": ex / 1e12, "peak": mufu_peak / 1e12, "unit": "Texp/s",
+                            "frac": ex / mufu_peak, "exp_per_chain_step": 21 * nodes, "per": "GPU",
+                            "peak_source": "live MUFU.EX2 probe (hepmc_mufu_probe)",
+                            "tensor_pipe": "sm__pipe_tensor_cycles_active 30.5 % in the ncu capture of hmc_tc_kernel "
+                                           "(profiles/r01_hmc_tc_kernel_ncu_summary.txt)" if ran in ("tc", "tc32") else None}
+                key = "hmc_elm%d_%s%s" % (nodes, prec, "_ridge" if ridge else "")
+                out[key] = {"metric": "camel-8D HMC+ELM chain-steps/s", "value": rate, "nodes": nodes,
+                            "surrogate": "trained: extreme_learning_train on 4000 points, ridge=%g" % ridge,
+                            "gradient_cancellation": grad.cancellation(x0h[:256]) , "precision_requested": prec,
+                            "kernel_ran": ran, "acceptance": acc, "roofline": roof,
+                            "cpu_baseline": cpu.get("hmc_elm%d" % nodes)}
     return out
 
 

@@ -52,6 +52,7 @@ SIGNATURES = {
     "hepmc_last_error": (ctypes.c_char_p, []),
     "hepmc_device_info": (_int, [_int, ctypes.POINTER(_i64)]),
     "hepmc_fp64_probe": (_int, [_i64, ctypes.POINTER(_dbl), ctypes.POINTER(_dbl), _vp]),
+    "hepmc_mufu_probe": (_int, [_i64, ctypes.POINTER(_dbl), ctypes.POINTER(_dbl), _vp]),
     "hepmc_density_eval": (_int, [_dens_p, _int, _vp, _i64, _vp, _vp]),
     "hepmc_default_chunk": (_i64, [_i64]),
     "hepmc_plain_mc_sample": (_int, [_dens_p, _i64, _i64, _i64, _u64, _u32, _int, _vp, _vp, _vp, _vp, _vp]),
@@ -201,3 +202,11 @@ def fp64_probe(iters=1 << 15):
     ms, fl = ctypes.c_double(), ctypes.c_double()
     check(load().hepmc_fp64_probe(int(iters), ctypes.byref(ms), ctypes.byref(fl), stream_ptr()), "fp64_probe")
     return fl.value / (ms.value * 1e-3)
+
+
+def mufu_probe(iters=1 << 15):
+    """Measured MUFU.EX2 throughput in exponentials/s (roofline denominator of the f32 / tensor-core ELM kernels)."""
+    require_cuda()
+    ms, ops = ctypes.c_double(), ctypes.c_double()
+    check(load().hepmc_mufu_probe(int(iters), ctypes.byref(ms), ctypes.byref(ops), stream_ptr()), "mufu_probe")
+    return ops.value / (ms.value * 1e-3)

@@ -215,15 +215,16 @@ class GridVolumes(Distribution):
             start += int(c)
 
     # ---- density ----------------------------------------------------------------
-    def _count_factor(self, idx):
-        """count(bin) / default_base_count for (ndim, N) bin indices on any device."""
-        fac = torch.ones(idx.shape[1], dtype=torch.float64, device=idx.device)
+    def _counts(self, idx):
+        """Base count of the bins with (ndim, N) indices, on any device (stratified_volume.py:57-65):
+        default_base_count, overwritten for the listed bins -- a default of 0 with explicit counts is valid."""
+        cnt = torch.full((idx.shape[1],), float(self.default_base_count), dtype=torch.float64, device=idx.device)
         for key, value in self.base_counts.items():
             hit = torch.ones(idx.shape[1], dtype=torch.bool, device=idx.device)
             for d in range(self.ndim):
                 hit &= idx[d] == int(key[d])
-            fac = torch.where(hit, torch.full_like(fac, value / self.default_base_count), fac)
-        return fac
+            cnt = torch.where(hit, torch.full_like(cnt, float(value)), cnt)
+        return cnt
 
     def pdf_indices(self, indices):
         """count / total_base_count / volume of the given bins (:67-72)."""
@@ -232,7 +233,7 @@ class GridVolumes(Distribution):
         vols = torch.ones(idx.shape[1], dtype=torch.float64)
         for d in range(self.ndim):
             vols = vols * sz[d][idx[d]]
-        out = self.default_base_count * self._count_factor(idx) / self.total_base_count / vols
+        out = self._counts(idx) / self.total_base_count / vols
         return out.numpy()
 
     def pdf(self, xs):
@@ -249,7 +250,7 @@ class GridVolumes(Distribution):
             for d in range(self.ndim):
                 vols = vols * (b[d][idx[d] + 1] - b[d][idx[d]])
             inside = ((x_dev > 0) & (x_dev < 1)).all(dim=1)
-            out = self.default_base_count * self._count_factor(idx) / self.total_base_count / vols
+            out = self._counts(idx) / self.total_base_count / vols
             return _lib.to_host_like(torch.where(inside, out, torch.zeros_like(out)), host)
         out = torch.empty(x_dev.shape[0], dtype=torch.float64, device=x_dev.device)
         if x_dev.shape[0]:
@@ -261,7 +262,7 @@ class GridVolumes(Distribution):
                 k = self.divisions
                 idx = torch.stack([torch.bucketize(x_dev[:, d].contiguous(), grid[d, :k + 1].contiguous(), right=True) - 1
                                    for d in range(self.ndim)]).clamp_(0, k - 1)
-                out = out * (self.default_base_count * self.partition_count / self.total_base_count) * self._count_factor(idx)
+                out = out * (self.partition_count / self.total_base_count) * self._counts(idx)
         return _lib.to_host_like(out, host)
 
     def pdf_gradient(self, xs):

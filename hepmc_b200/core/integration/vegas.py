@@ -32,6 +32,10 @@ class VegasSample(IntegrationSample):
 class VegasMC(object):
 
     def __init__(self, ndim=1, divisions=1, c=3, name="MC VEGAS", var_weighted=False):
+        if not (1 <= int(ndim) <= _lib.MAX_DIM):
+            raise ValueError("VegasMC supports 1 <= ndim <= %d (got %r)" % (_lib.MAX_DIM, ndim))
+        if not (1 <= int(divisions) <= 255):
+            raise ValueError("VegasMC supports 1 <= divisions <= 255 (bin ids are bytes in the kernels; got %r)" % (divisions,))
         self.ndim = ndim
         self.volumes = GridVolumes(ndim=ndim, divisions=divisions)
         self.divisions = divisions

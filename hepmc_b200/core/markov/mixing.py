@@ -51,6 +51,10 @@ def run_mc3(dens, channels, beta, local, x0, sample_size, thin, store_chain, fir
                 raise TypeError("a replaced pot_gradient must be a surrogate.SurrogateGradient")
             elm_blk, keep = grad.block()
         prec = {"f64": 0, "f32": 1}.get(local.precision, 0) if elm_blk is not None else 0
+        if elm_blk is not None and local.precision in ("tc", "tc32"):
+            import warnings
+            warnings.warn("the (MC)^3 mixing kernel has no tensor-core gradient: precision=%r of the local "
+                          "HamiltonianUpdate runs as 'f64' here" % local.precision, RuntimeWarning, stacklevel=3)
     elif isinstance(local, DefaultMetropolis) and isinstance(local._proposal, GaussianProposal):
         cov = np.asarray(local._proposal.cov)
         if np.count_nonzero(cov - np.diag(np.diagonal(cov))):

@@ -69,8 +69,14 @@ __global__ void __launch_bounds__(128) rwm_kernel(const __grid_constant__ Dens d
             }
             const double cpdf = density_pdf_n<NDIM>(dens, cand);
             const double ratio = cpdf / pdf;  // metropolis.py:50
-            // native mode: the accept uniform comes from the spare bits of the proposal draw (common.cuh)
-            const double u = a.u_replay ? a.u_replay[(size_t)c * (a.T - 1) + (t - 1)] : u_spare;
+            // native mode: the accept uniform comes from the spare bits of the proposal draw (common.cuh: 24 bits);
+            // small ratios, where 2^-24 steps would quantise the acceptance probability noticeably (and ratios
+            // below 3e-8 could never be accepted), take a full 52-bit uniform from the step's reserved Philox call
+            double u = a.u_replay ? a.u_replay[(size_t)c * (a.T - 1) + (t - 1)] : u_spare;
+            if (!a.u_replay && ratio < 0x1p-12) {
+                const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(t - 1) * CPS + NCALL, a.stream_id, key);
+                u = u52(r.x, r.y);
+            }
             if (ratio >= 1.0 || u < ratio) {  // metropolis.py:87 (NaN -> reject)
                 bool changed = false;
 #pragma unroll

@@ -45,6 +45,26 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(int64_t iters, double s
     if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
 }
 
+// 8 independent ex2.approx chains per thread (MUFU.EX2): the special-function roofline of the float32 /
+// tensor-core surrogate kernels, whose binding unit is one exponential per (chain, node, gradient).
+__global__ void __launch_bounds__(256) mufu_probe_kernel(int64_t iters, float seed, float* sink) {
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = seed + 0.001f * (threadIdx.x + i);
+    for (int64_t it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float r;
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a[i]));
+            a[i] = r - 1.0f;          // keeps the argument in (-1, 1): one FADD per exponential
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == 123.456f) sink[0] = s;
+}
+
 }  // namespace hepmc
 
 extern "C" {
@@ -87,6 +107,31 @@ int hepmc_fp64_probe(int64_t iters, double* ms_out, double* flops_out, void* str
     HEPMC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     *ms_out = ms;
     *flops_out = 16.0 * (double)iters * 256.0 * (double)blocks;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+int hepmc_mufu_probe(int64_t iters, double* ms_out, double* ops_out, void* stream) {
+    HEPMC_REQUIRE(ms_out && ops_out && iters > 0, HEPMC_E_ARG, "hepmc_mufu_probe: bad arguments");
+    cudaStream_t st = hepmc::as_stream(stream);
+    const int blocks = hepmc::sm_count() * 8;
+    float* sink = nullptr;
+    HEPMC_CUDA(cudaMalloc(&sink, sizeof(float)));
+    cudaEvent_t e0, e1;
+    HEPMC_CUDA(cudaEventCreate(&e0));
+    HEPMC_CUDA(cudaEventCreate(&e1));
+    hepmc::mufu_probe_kernel<<<blocks, 256, 0, st>>>(iters / 8 + 1, 0.5f, sink);  // warm-up
+    HEPMC_CUDA(cudaEventRecord(e0, st));
+    hepmc::mufu_probe_kernel<<<blocks, 256, 0, st>>>(iters, 0.5f, sink);
+    HEPMC_CUDA(cudaEventRecord(e1, st));
+    HEPMC_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    HEPMC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms;
+    *ops_out = 8.0 * (double)iters * 256.0 * (double)blocks;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(sink);

@@ -48,6 +48,22 @@ class HamiltonianUpdate(MetropolisUpdate):
         pass
 
     @property
+    def precision(self):
+        return self._precision
+
+    @precision.setter
+    def precision(self, value):
+        if value not in ("f64", "f32", "tc", "tc32"):
+            raise ValueError("precision must be 'f64', 'f32', 'tc' or 'tc32'")
+        self._precision = value
+        self._tc_key = None            # forget the tc / tc32 decision taken for the previous setting
+
+    @property
+    def kernel_precision(self):
+        """The surrogate arithmetic the last sample() call actually ran ('tc' may have switched to 'tc32')."""
+        return getattr(self, "_ran_precision", None)
+
+    @property
     def step_size(self):
         return self.simulate.step_size
 
@@ -109,7 +125,11 @@ class HamiltonianUpdate(MetropolisUpdate):
         if prec == 2:
             # TF32 operands in the contraction cannot resolve a heavily cancelling weight vector:
             # measure the cancellation once and fall back to the FP32 contraction ("tc32") above the limit
-            if getattr(self, "_tc_mode", None) is None:
+            # the decision belongs to ONE surrogate (its weights) and to this precision setting: a re-trained or
+            # re-attached surrogate is measured again
+            key = (id(grad), id(grad.out_weights))
+            if getattr(self, "_tc_key", None) != key:
+                self._tc_key = key
                 kappa = grad.cancellation(x0[:256])
                 self._tc_mode = 3 if kappa > TC_CANCELLATION_LIMIT else 2
                 if self._tc_mode == 3:
@@ -119,6 +139,7 @@ class HamiltonianUpdate(MetropolisUpdate):
                                   "FP32 contraction) instead.  extreme_learning_train(..., ridge=1e-6) avoids the "
                                   "cancellation." % (kappa, TC_CANCELLATION_LIMIT), RuntimeWarning, stacklevel=3)
             prec = self._tc_mode
+        self._ran_precision = ("f64", "f32", "tc", "tc32")[prec]
         out = ensemble.run_hmc(tgt._block(), elm_blk, prec, x0, mass, self.step_size, self.steps,
                                sample_size, thin, store_chain, first_chain, None, replay,
                                getattr(self, "_total_chains", None))

@@ -88,6 +88,10 @@ int hepmc_device_info(int device, int64_t* out5);
  * `iters` dependent-chain rounds of 8 independent DFMAs per thread on a full grid, and
  * returns the elapsed milliseconds (CUDA events, synchronises) and the flop count. */
 int hepmc_fp64_probe(int64_t iters, double* ms_out, double* flops_out, void* stream);
+/* MUFU.EX2 micro-benchmark (8 independent ex2.approx chains per thread, full grid): elapsed milliseconds
+ * and the number of exponentials; the special-function roofline of the float32 / tensor-core surrogate
+ * kernels (one exponential per chain, node and gradient evaluation). */
+int hepmc_mufu_probe(int64_t iters, double* ms_out, double* ops_out, void* stream);
 
 /* ---- native generator --------------------------------------------------------------
  * The integrators' native draws (the counterpart of np.random.randint / np.random.rand in

@@ -200,3 +200,25 @@ def test_sample_summaries_single_chain_and_ensemble():
     assert np.allclose(ens.mean, ens.data.reshape(-1, 3).mean(axis=0))
     assert np.allclose(ens.variance, ens.data.reshape(-1, 3).var(axis=0))
     assert H.core.sampling.Sample().size is None and "N/A" in repr(H.core.sampling.Sample())
+
+
+def test_vegas_argument_validation_is_at_construction():
+    import hepmc_b200 as H
+    with pytest.raises(ValueError):
+        H.VegasMC(2, divisions=256)
+    with pytest.raises(ValueError):
+        H.VegasMC(33, divisions=4)
+    H.VegasMC(32, divisions=255)
+
+
+def test_rng_modes_host_state():
+    import hepmc_b200 as H
+    assert H.rng.get_mode() == H.rng.DEFAULT_MODE == "u32r10" and H.rng.mode_code() == 1
+    H.rng.set_mode("u52r10")
+    assert H.rng.mode_code() == 0
+    H.seed(5)                                   # the mode is a setting, not part of the seed state
+    assert H.rng.get_mode() == "u52r10"
+    with pytest.raises(ValueError):
+        H.rng.set_mode("u16r1")
+    H.rng.set_mode()
+    assert H.rng.get_mode() == "u32r10"

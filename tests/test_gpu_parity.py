@@ -525,7 +525,8 @@ def test_uniform_local_metropolis():
     w = O.philox_words(77, 0, 7 + np.arange(C), 2 * (T - 1)).astype(np.uint32)
     vv = O.u52(w[:, 0::2, 0], w[:, 0::2, 1])
     uu = O.u24_spare(w[:, 0::2, 0], w[:, 0::2, 2])
-    chain, acc = O.uniform_local_chains(O.camel_pdf, x0, vv, uu, delta)
+    ur = O.u52(w[:, 1::2, 0], w[:, 1::2, 1])                 # ratios < 2^-12: full uniform of the step's second call
+    chain, acc = O.uniform_local_chains(O.camel_pdf, x0, vv, uu, delta, u_rare=ur)
     assert np.array_equal(s.accepted, acc)
     assert_close(s.data, chain, 1e-12, atol=1e-15)
     assert s.data.min() >= 0.0 and s.data.max() <= 1.0       # the box is pushed back into [0, 1]
@@ -547,11 +548,13 @@ def test_metropolis_native_matches_oracle_draws():
     w = O.philox_words(31337, 0, idx, 2 * (T - 1)).astype(np.uint32)
     z = np.empty((C, T - 1, 2))
     u = np.empty((C, T - 1))
+    u_rare = np.empty((C, T - 1))
     for t in range(T - 1):
         z0, z1 = O.box_muller(O.u52(w[:, 2 * t, 0], w[:, 2 * t, 1]), O.u52(w[:, 2 * t, 2], w[:, 2 * t, 3]))
         z[:, t, 0], z[:, t, 1] = z0, z1
         u[:, t] = O.u24_spare(w[:, 2 * t, 0], w[:, 2 * t, 2])
-    chain, acc = O.metropolis_chains(O.banana_pdf, x0, z, u, np.sqrt([10., 10.]))
+        u_rare[:, t] = O.u52(w[:, 2 * t + 1, 0], w[:, 2 * t + 1, 1])    # ratios < 2^-12: the step's second call
+    chain, acc = O.metropolis_chains(O.banana_pdf, x0, z, u, np.sqrt([10., 10.]), u_rare=u_rare)
     assert np.array_equal(s.accepted, acc)
     assert_close(s.data, chain, 1e-10, atol=1e-10)
 
@@ -1148,8 +1151,8 @@ def test_edge_cases_maximum_sizes():
     r = O.vegas(O.camel_pdf, 2, 255, np.stack([t[0] for t in tapes]), np.stack([t[1] for t in tapes]))
     assert_close(s.estimates, r["est_j"], RTOL)
     assert_close(np.stack(mc.volumes.bounds), r["bounds_history"][-1], 1e-11, atol=1e-15)
-    with pytest.raises(RuntimeError):
-        H.VegasMC(2, divisions=256)(H.densities.Camel(2), 100, 1)
+    with pytest.raises(ValueError):                          # a clear error at construction (bin ids are bytes)
+        H.VegasMC(2, divisions=256)
     # chains at ndim = 16 (HEPMC_MAX_CHAIN_DIM)
     H.seed(7)
     C, T, nd = 33, 40, 16
@@ -1163,7 +1166,8 @@ def test_edge_cases_maximum_sizes():
             z0, z1 = O.box_muller(O.u52(w[:, 9 * t + k, 0], w[:, 9 * t + k, 1]), O.u52(w[:, 9 * t + k, 2], w[:, 9 * t + k, 3]))
             z[:, t, 2 * k], z[:, t, 2 * k + 1] = z0, z1
         u[:, t] = O.u24_spare(w[:, 9 * t, 0], w[:, 9 * t, 2])      # spare bits of the step's first proposal call
-    chain, acc = O.metropolis_chains(lambda x: O.gaussian_pdf(x, 0.5, 0.01), x0, z, u, np.full(nd, 0.02))
+    ur = O.u52(w[:, 8::9, 0], w[:, 8::9, 1])                       # ratios < 2^-12: the step's ninth call
+    chain, acc = O.metropolis_chains(lambda x: O.gaussian_pdf(x, 0.5, 0.01), x0, z, u, np.full(nd, 0.02), u_rare=ur)
     assert np.array_equal(s.accepted, acc)
     assert_close(s.data, chain, 1e-10, atol=1e-12)
     with pytest.raises(RuntimeError):
