@@ -66,6 +66,10 @@ SIGNATURES = {
     "hepmc_reduce_slots_scratch_bytes": (_i64, [_int, _int]),
     "hepmc_reduce_slots": (_int, [_vp, _vp, ctypes.POINTER(_i64), _int, _int, _vp, _vp, _vp]),
     "hepmc_vegas_update_grid_packed": (_int, [_vp, _int, _vp, _int, _int, _dbl, _int, _vp, _vp]),
+    "hepmc_slot_exchange_bytes": (_i64, [_int]),
+    "hepmc_reduce_slots_p2p": (_int, [_vp, _vp, ctypes.POINTER(_i64), _int, _int, _vp, _vp, ctypes.POINTER(_i64), _int, _int,
+                                      _u64, _vp]),
+    "hepmc_vegas_update_grid_p2p": (_int, [_vp, _int, _u64, _vp, _int, _int, _dbl, _int, _vp, _vp, _vp]),
     "hepmc_vegas_workspace_bytes": (_i64, [_int, _int, _i64]),
     "hepmc_vegas_integrate": (_int, [_dens_p, _vp, _int, _int, _i64, _int, _dbl, _u64, _u32, _int,
                                      _vp, _vp, _i64, _vp]),

@@ -114,6 +114,10 @@ class VegasMC(object):
         scratch = torch.zeros(int(_lib.load().hepmc_reduce_slots_scratch_bytes(n_slots_local, cols)) // 8 + 1,
                               dtype=torch.float64, device=dev)    # zero: arrival counters of the fused reduction
         begins_c = _lib.i64_array(begins)
+        # multi-GPU: the slot rows travel over NVLink peer memory inside the reduction / update kernels when a
+        # symmetric allocation is available (parallel.SlotExchange), else through one NCCL all-gather
+        exchange = parallel.SlotExchange.get(cols) if (ws > 1 and dev.type == "cuda") else None
+        slot0 = parallel.slot_span()[0] if ws > 1 else 0
         seed = rng.get_seed()
         sid0 = rng.next_stream(iterations)
         blk = dens._block() if fused else engine.none_block(ndim)
@@ -147,15 +151,25 @@ class VegasMC(object):
                     f = engine.call_integrand(fn, [x[d] for d in range(ndim)])
                     _lib.call("hepmc_vegas_accumulate", _lib.ptr(f), _lib.ptr(w), _lib.ptr(idx), ndim, K,
                               n_local, chunk, _lib.ptr(stats_p), _lib.ptr(hist_p), st)
-            _lib.call("hepmc_reduce_slots", _lib.ptr(stats_p), _lib.ptr(hist_p), begins_c, n_slots_local, cols,
-                      _lib.ptr(slot_local), _lib.ptr(scratch), st)
-            if ws > 1:
-                parallel.gather_slots(slot_local, out=slots_all)
-            _lib.call("hepmc_vegas_update_grid_packed", _lib.ptr(slots_all), slots_all.shape[0],
-                      _lib.ptr(grid), ndim, K, float(self.c), j, _lib.ptr(est_var), st)
+            if exchange is not None:
+                epoch = exchange.next_epoch()
+                _lib.call("hepmc_reduce_slots_p2p", _lib.ptr(stats_p), _lib.ptr(hist_p), begins_c, n_slots_local, cols,
+                          _lib.ptr(slot_local), _lib.ptr(scratch), exchange.peer_ptrs, ws, slot0, epoch, st)
+                _lib.call("hepmc_vegas_update_grid_p2p", _lib.ptr(exchange.buffer), cols, epoch, _lib.ptr(grid), ndim, K,
+                          float(self.c), j, _lib.ptr(est_var), _lib.ptr(exchange.timeout), st)
+            else:
+                _lib.call("hepmc_reduce_slots", _lib.ptr(stats_p), _lib.ptr(hist_p), begins_c, n_slots_local, cols,
+                          _lib.ptr(slot_local), _lib.ptr(scratch), st)
+                if ws > 1:
+                    parallel.gather_slots(slot_local, out=slots_all)
+                _lib.call("hepmc_vegas_update_grid_packed", _lib.ptr(slots_all), slots_all.shape[0],
+                          _lib.ptr(grid), ndim, K, float(self.c), j, _lib.ptr(est_var), st)
             if kept is not None and not fused and n_local:
                 kept["function_values"][j * n_local:(j + 1) * n_local] = f
-        return self._combine(est_var, n_total, iterations, chi, kept)
+        out = self._combine(est_var, n_total, iterations, chi, kept)
+        if exchange is not None:
+            exchange.check()
+        return out
 
     def _combine(self, est_var, n_total, iterations, chi, kept):
         """Combination of the iterations, vegas.py:124-142 (host scalars)."""

@@ -188,10 +188,28 @@ __device__ __forceinline__ void reduce_slots_l2(const double* __restrict__ in /*
     }
 }
 
+// Peer-memory exchange of the packed slot rows (the all-gather of the VEGAS iteration, fused into the reduction):
+// every rank owns a symmetric buffer  [2 parities][HEPMC_N_SLOTS][3 + ncols] doubles | [2][HEPMC_N_SLOTS] flags
+// mapped into all peers (NVLink P2P through NVSwitch).  The CTA that finishes a slot writes its packed row
+// straight into EVERY rank's buffer at the slot's global position and then publishes flag = epoch there
+// (release at system scope); the grid update of every rank waits for its 8 flags (vegas_update_kernel).
+// Two parities: a rank can be at most one iteration ahead of a peer (its next update waits for the peer's next
+// row), so the buffer a slow peer still reads is never the one being written.
+struct SlotPeers {
+    double* base[HEPMC_N_SLOTS];     // peer buffers (device pointers valid on this GPU); world <= 8
+    int world;
+    int slot0;                       // global index of this rank's first slot
+    unsigned long long epoch;        // iteration counter, > 0, the same on every rank
+};
+
+__device__ __forceinline__ unsigned long long* peer_flags(double* base, int ncols) {
+    return reinterpret_cast<unsigned long long*>(base + (size_t)2 * HEPMC_N_SLOTS * (3 + ncols));
+}
+
 __global__ void __launch_bounds__(kRedCols * kRedLanes) reduce_slots_kernel(
     const double* __restrict__ stats_rows, const double* __restrict__ hist_rows, const __grid_constant__ RowRanges rr,
     int ncols, double* __restrict__ scratch /* (n_out, G, 3 + ncols) */, unsigned int* __restrict__ counters /* n_out, zero */,
-    double* __restrict__ packed /* (n_out, 3 + ncols) */) {
+    double* __restrict__ packed /* (n_out, 3 + ncols) */, const __grid_constant__ SlotPeers peers) {
     __shared__ double part[kRedLanes][kRedCols];
     __shared__ Stats s_w[8];
     __shared__ bool s_last;
@@ -235,7 +253,22 @@ __global__ void __launch_bounds__(kRedCols * kRedLanes) reduce_slots_kernel(
     __syncthreads();
     if (s_last) {
         __threadfence();
-        reduce_slots_l2(scratch + (size_t)s * kSlotGroups * (3 + ncols), ncols, packed + (size_t)s * (3 + ncols));
+        double* mine = packed + (size_t)s * (3 + ncols);
+        reduce_slots_l2(scratch + (size_t)s * kSlotGroups * (3 + ncols), ncols, mine);
+        if (peers.world > 1) {
+            // publish: the row into every rank's buffer (plain stores over NVLink), then the flag
+            __syncthreads();
+            const int row = 3 + ncols;
+            const size_t at = ((size_t)(peers.epoch & 1) * HEPMC_N_SLOTS + peers.slot0 + s) * row;
+            for (int r = 0; r < peers.world; ++r)
+                for (int c = threadIdx.x; c < row; c += blockDim.x) peers.base[r][at + c] = mine[c];
+            __threadfence_system();
+            __syncthreads();
+            if ((int)threadIdx.x < peers.world) {
+                unsigned long long* f = peer_flags(peers.base[threadIdx.x], ncols) + (peers.epoch & 1) * HEPMC_N_SLOTS + peers.slot0 + s;
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(peers.epoch) : "memory");
+            }
+        }
     }
 }
 
@@ -245,15 +278,32 @@ __global__ void __launch_bounds__(kRedCols * kRedLanes) reduce_slots_kernel(
 __global__ void __launch_bounds__(256) vegas_update_kernel(const double* __restrict__ slot_stats, int64_t stats_stride,
                                                            const double* __restrict__ slot_hist, int64_t hist_stride,
                                                            int n_slots, double* __restrict__ grid, int ndim, int K,
-                                                           double c, int j, double* __restrict__ est_var) {
+                                                           double c, int j, double* __restrict__ est_var,
+                                                           const unsigned long long* __restrict__ wait_flags,
+                                                           unsigned long long epoch, int* __restrict__ timeout_flag) {
     extern __shared__ double sm[];
     double* s_new = sm;  // ndim*K new sizes
     __shared__ double s_est, s_n;
+    if (wait_flags != nullptr) {
+        // peer-memory exchange: slot s is complete when its flag carries this iteration's epoch.  Bounded spin
+        // (~4 s): a missing peer becomes an error code of the call, never a hung GPU.
+        if ((int)threadIdx.x < n_slots) {
+            const long long t0 = clock64();
+            unsigned long long v = 0;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(wait_flags + threadIdx.x) : "memory");
+                if (v >= epoch) break;
+                if (clock64() - t0 > 8000000000LL) { if (timeout_flag) *timeout_flag = 1 + (int)threadIdx.x; break; }
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         Stats t{0.0, 0.0, 0.0};
         for (int s = 0; s < n_slots; ++s) {
             const double* ss = slot_stats + (size_t)s * stats_stride;
-            Stats u{ss[0], ss[1], ss[2]};
+            Stats u{__ldcg(ss), __ldcg(ss + 1), __ldcg(ss + 2)};
             t = merge(t, u);
         }
         s_est = t.mean;               // est_j = mean(weighted)           vegas.py:110
@@ -268,7 +318,7 @@ __global__ void __launch_bounds__(256) vegas_update_kernel(const double* __restr
     for (int q = threadIdx.x; q < ndim * K; q += blockDim.x) {
         const int d = q / K, k = q % K;
         double h = 0.0;
-        for (int s = 0; s < n_slots; ++s) h += slot_hist[(size_t)s * hist_stride + q];
+        for (int s = 0; s < n_slots; ++s) h += __ldcg(slot_hist + (size_t)s * hist_stride + q);
         const double estimate = h / n;                       // vegas.py:108-109
         const double size = grid[d * stride + K + 1 + k];
         const double old_v = est / size;                     // vegas.py:113
@@ -563,7 +613,8 @@ int hepmc_vegas_update_grid(const double* slot_stats_dev, const double* slot_his
     const size_t smem = (size_t)ndim * divisions * 8;
     HEPMC_CUDA(cudaFuncSetAttribute(vegas_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     vegas_update_kernel<<<1, 256, smem, as_stream(stream)>>>(slot_stats_dev, 3, slot_hist_dev, (int64_t)ndim * divisions,
-                                                             n_slots, grid_dev, ndim, divisions, c, j, est_var_dev);
+                                                             n_slots, grid_dev, ndim, divisions, c, j, est_var_dev, nullptr, 0,
+                                                             nullptr);
     HEPMC_LAUNCH_CHECK();
     return 0;
 }
@@ -583,8 +634,57 @@ int hepmc_reduce_slots(const double* stats_rows_dev, const double* hist_rows_dev
     dim3 grid(ntile + 1, kSlotGroups, n_out);
     double* partials = reinterpret_cast<double*>(scratch_dev);
     unsigned int* counters = reinterpret_cast<unsigned int*>(partials + (size_t)n_out * kSlotGroups * (3 + ncols));
+    SlotPeers none{};
+    none.world = 1;
     reduce_slots_kernel<<<grid, kRedCols * kRedLanes, 0, as_stream(stream)>>>(stats_rows_dev, hist_rows_dev, rr, ncols,
-                                                                              partials, counters, packed_dev);
+                                                                              partials, counters, packed_dev, none);
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t hepmc_slot_exchange_bytes(int ncols) {
+    return (int64_t)2 * HEPMC_N_SLOTS * (3 + ncols) * 8 + (int64_t)2 * HEPMC_N_SLOTS * 8;
+}
+
+int hepmc_reduce_slots_p2p(const double* stats_rows_dev, const double* hist_rows_dev, const int64_t* row_begin_host,
+                           int n_out, int ncols, double* packed_dev, void* scratch_dev,
+                           const int64_t* peer_buffers_host, int world, int first_slot, uint64_t epoch, void* stream) {
+    RowRanges rr;
+    int e = fill_ranges(rr, row_begin_host, n_out, "hepmc_reduce_slots_p2p");
+    if (e) return e;
+    HEPMC_REQUIRE(stats_rows_dev && hist_rows_dev && packed_dev && scratch_dev && ncols >= 1 && peer_buffers_host, HEPMC_E_ARG,
+                  "hepmc_reduce_slots_p2p: bad arguments");
+    HEPMC_REQUIRE(world >= 2 && world <= HEPMC_N_SLOTS && first_slot >= 0 && first_slot + n_out <= HEPMC_N_SLOTS && epoch > 0,
+                  HEPMC_E_ARG, "hepmc_reduce_slots_p2p: world %d / first_slot %d / epoch out of range", world, first_slot);
+    SlotPeers peers{};
+    for (int r = 0; r < world; ++r) {
+        HEPMC_REQUIRE(peer_buffers_host[r] != 0, HEPMC_E_ARG, "hepmc_reduce_slots_p2p: peer buffer %d is NULL", r);
+        peers.base[r] = reinterpret_cast<double*>((uintptr_t)peer_buffers_host[r]);
+    }
+    peers.world = world; peers.slot0 = first_slot; peers.epoch = epoch;
+    const int ntile = (ncols + kRedCols - 1) / kRedCols;
+    dim3 grid(ntile + 1, kSlotGroups, n_out);
+    double* partials = reinterpret_cast<double*>(scratch_dev);
+    unsigned int* counters = reinterpret_cast<unsigned int*>(partials + (size_t)n_out * kSlotGroups * (3 + ncols));
+    reduce_slots_kernel<<<grid, kRedCols * kRedLanes, 0, as_stream(stream)>>>(stats_rows_dev, hist_rows_dev, rr, ncols,
+                                                                              partials, counters, packed_dev, peers);
+    HEPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+int hepmc_vegas_update_grid_p2p(const double* exchange_dev, int ncols, uint64_t epoch, double* grid_dev, int ndim,
+                                int divisions, double c, int j, double* est_var_dev, int* timeout_flag_dev, void* stream) {
+    HEPMC_REQUIRE(exchange_dev && grid_dev && est_var_dev && epoch > 0, HEPMC_E_ARG, "hepmc_vegas_update_grid_p2p: bad arguments");
+    HEPMC_REQUIRE(ndim >= 1 && ndim <= HEPMC_MAX_DIM && divisions >= 1 && j >= 0 && ncols == ndim * divisions, HEPMC_E_ARG,
+                  "hepmc_vegas_update_grid_p2p: bad sizes");
+    const size_t smem = (size_t)ndim * divisions * 8;
+    const int64_t row = 3 + (int64_t)ncols;
+    const double* packed = exchange_dev + (size_t)(epoch & 1) * HEPMC_N_SLOTS * row;
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(exchange_dev + (size_t)2 * HEPMC_N_SLOTS * row) +
+                                      (epoch & 1) * HEPMC_N_SLOTS;
+    HEPMC_CUDA(cudaFuncSetAttribute(vegas_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vegas_update_kernel<<<1, 256, smem, as_stream(stream)>>>(packed, row, packed + 3, row, HEPMC_N_SLOTS, grid_dev, ndim,
+                                                             divisions, c, j, est_var_dev, flags, epoch, timeout_flag_dev);
     HEPMC_LAUNCH_CHECK();
     return 0;
 }
@@ -598,7 +698,7 @@ int hepmc_vegas_update_grid_packed(const double* packed_dev, int n_slots, double
     const int64_t row = 3 + (int64_t)ndim * divisions;
     HEPMC_CUDA(cudaFuncSetAttribute(vegas_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     vegas_update_kernel<<<1, 256, smem, as_stream(stream)>>>(packed_dev, row, packed_dev + 3, row, n_slots, grid_dev, ndim,
-                                                             divisions, c, j, est_var_dev);
+                                                             divisions, c, j, est_var_dev, nullptr, 0, nullptr);
     HEPMC_LAUNCH_CHECK();
     return 0;
 }

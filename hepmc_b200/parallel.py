@@ -73,3 +73,66 @@ def sum_int(value_tensor):
     if ws > 1:
         dist.all_reduce(value_tensor, op=dist.ReduceOp.SUM)
     return value_tensor
+
+
+# ---------------------------------------------------------------------------------------------
+# Peer-memory slot exchange (multi-GPU VEGAS): the all-gather of the 8 packed slot rows done by the
+# reduction kernel itself with plain stores into every peer's buffer over NVLink, and awaited by the
+# grid-update kernel through per-slot flags (C ABI: hepmc_reduce_slots_p2p, hepmc_vegas_update_grid_p2p).
+# PyTorch only provides the plumbing: a symmetric allocation mapped into all ranks of the node.
+# HEPMC_B200_EXCHANGE = "p2p" (require it), "nccl" (never use it), "auto" (default: p2p if the
+# symmetric allocation works, else NCCL's all-gather).
+# ---------------------------------------------------------------------------------------------
+class SlotExchange(object):
+    _cache = {}
+
+    def __init__(self, ncols):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        rank, ws = world()
+        nbytes = int(_lib.load().hepmc_slot_exchange_bytes(int(ncols)))
+        self.ncols = int(ncols)
+        self.buffer = symm_mem.empty(nbytes // 8, dtype=torch.float64, device=_lib.device())
+        self.buffer.zero_()
+        self.handle = symm_mem.rendezvous(self.buffer, dist.group.WORLD)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(ptrs) != ws or any(p == 0 for p in ptrs):
+            raise RuntimeError("symmetric memory rendezvous returned %d peer pointers for %d ranks" % (len(ptrs), ws))
+        self.peer_ptrs = _lib.i64_array(ptrs)
+        self.timeout = torch.zeros(1, dtype=torch.int32, device=_lib.device())
+        self.epoch = 0
+        torch.cuda.synchronize()
+        dist.barrier()                       # every buffer is zeroed before anyone stores into it
+
+    def next_epoch(self):
+        self.epoch += 1
+        return self.epoch
+
+    def check(self):
+        """After the call's final synchronisation: did a grid update give up waiting for a peer?"""
+        t = int(self.timeout.item())
+        if t:
+            self.timeout.zero_()
+            raise RuntimeError("hepmc_b200: the peer-memory slot exchange timed out waiting for slot %d "
+                               "(a rank of the job did not reach the same VEGAS iteration)" % (t - 1))
+
+    @classmethod
+    def get(cls, ncols):
+        """The exchange for rows of `ncols` histogram columns, or None (-> NCCL all-gather)."""
+        import os
+        import sys
+        mode = os.environ.get("HEPMC_B200_EXCHANGE", "auto").lower()
+        rank, ws = world()
+        if ws == 1 or mode == "nccl" or N_SLOTS % ws:
+            return None
+        if ncols not in cls._cache:
+            try:
+                cls._cache[ncols] = cls(ncols)
+            except Exception as exc:        # no symmetric memory on this system / backend
+                if mode == "p2p":
+                    raise
+                if rank == 0:
+                    sys.stderr.write("hepmc_b200: peer-memory slot exchange unavailable (%s: %s); using the NCCL "
+                                     "all-gather\n" % (type(exc).__name__, exc))
+                cls._cache[ncols] = None
+        return cls._cache[ncols]

@@ -197,6 +197,24 @@ int hepmc_reduce_slots(const double* stats_rows_dev, const double* hist_rows_dev
 int hepmc_vegas_update_grid_packed(const double* packed_dev, int n_slots, double* grid_dev, int ndim, int divisions,
                                    double c, int j, double* est_var_dev, void* stream);
 
+/* ---- the same exchange over NVLink peer memory, fused into the two kernels (multi-GPU VEGAS) ----------
+ * Every rank owns an EXCHANGE buffer of hepmc_slot_exchange_bytes(ncols) bytes, zero-initialised, mapped
+ * into all peers of the node (e.g. torch.distributed._symmetric_memory): [2 parities][8 slots][3 + ncols]
+ * doubles followed by [2][8] 64-bit flags.  hepmc_reduce_slots_p2p = hepmc_reduce_slots whose last CTA of
+ * each slot also stores the packed row into EVERY rank's buffer (peer_buffers_host[r], r < world, pointers
+ * valid on this GPU) at the slot's global position (first_slot + local index) and then releases
+ * flag = epoch there.  hepmc_vegas_update_grid_p2p = the grid update on this rank's own buffer, waiting
+ * (bounded spin; *timeout_flag_dev != 0 afterwards means a peer never arrived) until all 8 flags of the
+ * parity carry `epoch`.  epoch: iteration counter > 0, equal on all ranks, increasing by one per
+ * iteration over the life of the buffer.  No NCCL call, no host synchronisation: replaces the all-gather
+ * of vegas.py:108-111's sums across GPUs. */
+int64_t hepmc_slot_exchange_bytes(int ncols);
+int hepmc_reduce_slots_p2p(const double* stats_rows_dev, const double* hist_rows_dev, const int64_t* row_begin_host,
+                           int n_out, int ncols, double* packed_dev, void* scratch_dev,
+                           const int64_t* peer_buffers_host, int world, int first_slot, uint64_t epoch, void* stream);
+int hepmc_vegas_update_grid_p2p(const double* exchange_dev, int ncols, uint64_t epoch, double* grid_dev, int ndim,
+                                int divisions, double c, int j, double* est_var_dev, int* timeout_flag_dev, void* stream);
+
 /* Workspace (bytes) hepmc_vegas_integrate needs for n points per iteration. */
 int64_t hepmc_vegas_workspace_bytes(int ndim, int divisions, int64_t n);
 /* Whole single-GPU VegasMC.__call__ (vegas.py:74-118): `iterations` x (sample, slot

@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = r'''
 import os, sys, json
 sys.path.insert(0, %r)
+ROOTDIR = sys.path[0]
 import numpy as np, torch, torch.distributed as dist
 import hepmc_b200 as H
 ws = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
@@ -44,6 +45,25 @@ acc = ms.total_accepted.clone()
 H.parallel.sum_int(acc)
 out["rwm_total_accepted"] = int(acc.item())
 out["rwm_last_sum"] = float(ms.data.sum().item()) if ws == 1 else None
+# surrogate-gradient HMC: the cooperative / thread-per-chain layout follows the GLOBAL ensemble size, so the
+# chains are bit-identical however they are sharded (600 chains: one call at 1 rank, 2 x 300 at 2 ranks)
+e = dict(np.load(os.path.join(ROOTDIR, "tests", "golden", "elm.npz")))
+tgt = H.densities.Camel(8)
+H.surrogate.attach_surrogate_gradient(tgt, H.surrogate.GaussianBasis(8), (e["g100_centers"], e["g100_widths"], None),
+                                      float(e["g100_bias"]), e["g100_weights"])
+C = 600
+first, count = H.parallel.item_span(C)
+x0 = (1 / 3 + 0.05 * np.random.default_rng(3).standard_normal((C, 8)))[first:first + count]
+H.seed(21)
+hs = H.hamiltonian.HamiltonianUpdate(tgt, H.densities.Gaussian(8, cov=10.), 10, 0.1).sample(8, x0, store_chain=False, first_chain=first)
+last = hs.data[:, 0].contiguous()
+if ws > 1:
+    parts = [torch.empty_like(last) for _ in range(ws)]
+    dist.all_gather(parts, last)
+    last = torch.cat(parts)
+out["hmc_elm_last"] = last.cpu().numpy().ravel().tolist()
+ex = H.parallel.SlotExchange._cache
+out["exchange"] = "p2p" if any(v is not None for v in ex.values()) else "nccl"
 if rank == 0:
     print("RESULT " + json.dumps(out))
 if ws > 1:
@@ -51,7 +71,7 @@ if ws > 1:
 '''
 
 
-def _run(nproc):
+def _run(nproc, exchange="auto"):
     code = WORKER % ROOT
     path = os.path.join(ROOT, "gpurun_out", "_multi_worker.py")
     os.makedirs(os.path.dirname(path), exist_ok=True)
@@ -62,7 +82,8 @@ def _run(nproc):
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
                "--master-addr", "127.0.0.1", "--master-port", "29533", path]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    env = dict(os.environ, HEPMC_B200_EXCHANGE=exchange)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert res.returncode == 0, res.stderr[-2000:]
     line = [l for l in res.stdout.splitlines() if l.startswith("RESULT ")][-1]
     return json.loads(line[len("RESULT "):])
@@ -70,7 +91,12 @@ def _run(nproc):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_results_are_bit_identical_at_one_and_two_ranks():
-    one, two = _run(1), _run(2)
-    for key in ("plain", "vegas", "rambo_is", "multichannel"):
+    one, two, two_nccl = _run(1), _run(2), _run(2, "nccl")
+    for key in ("plain", "vegas", "rambo_is", "multichannel", "hmc_elm_last"):
         assert one[key] == two[key], key
+        assert one[key] == two_nccl[key], key
     assert one["rwm_total_accepted"] == two["rwm_total_accepted"]
+    # the peer-memory exchange (NVLink stores + flags inside the kernels) and NCCL's all-gather are two transports
+    # of the same packed slot rows
+    assert two_nccl["exchange"] == "nccl"
+    print("slot exchange at 2 ranks:", two["exchange"])
