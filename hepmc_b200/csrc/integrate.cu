@@ -171,20 +171,24 @@ constexpr int kRedCols = 32, kRedLanes = 8;
 // and the combine order is fixed whichever CTA runs it.
 __device__ __forceinline__ void reduce_slots_l2(const double* __restrict__ in /* (G, 3 + ncols) */, int ncols,
                                                 double* __restrict__ out /* (3 + ncols) */) {
+    static_assert(kSlotGroups == 32, "the group statistics are merged by one warp, one group per lane");
     const int row = 3 + ncols;
-    for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
-        double acc = 0.0;
-#pragma unroll 8
-        for (int g = 0; g < kSlotGroups; ++g) acc += __ldcg(in + (size_t)g * row + 3 + c);
-        out[3 + c] = acc;
+    // the group statistics first: lane g of warp 0 loads group g (all loads in flight at once -- a single thread
+    // walking the 32 groups paid an L2 round trip per group: 13 us), merged in the fixed butterfly of warp_merge
+    if (threadIdx.x < 32) {
+        const double* gs = in + (size_t)threadIdx.x * row;
+        Stats u{__ldcg(gs), __ldcg(gs + 1), __ldcg(gs + 2)};
+        const Stats t = warp_merge(u);
+        if (threadIdx.x == 0) { out[0] = t.n; out[1] = t.mean; out[2] = t.m2; }
     }
-    if (threadIdx.x == 0) {
-        Stats t{0.0, 0.0, 0.0};
-        for (int g = 0; g < kSlotGroups; ++g) {
-            Stats u{__ldcg(in + (size_t)g * row), __ldcg(in + (size_t)g * row + 1), __ldcg(in + (size_t)g * row + 2)};
-            t = merge(t, u);
-        }
-        out[0] = t.n; out[1] = t.mean; out[2] = t.m2;
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+        double v[kSlotGroups];
+#pragma unroll
+        for (int g = 0; g < kSlotGroups; ++g) v[g] = __ldcg(in + (size_t)g * row + 3 + c);   // 32 independent loads
+        double acc = 0.0;
+#pragma unroll
+        for (int g = 0; g < kSlotGroups; ++g) acc += v[g];                                  // group order
+        out[3 + c] = acc;
     }
 }
 
@@ -284,6 +288,7 @@ __global__ void __launch_bounds__(256) vegas_update_kernel(const double* __restr
     extern __shared__ double sm[];
     double* s_new = sm;  // ndim*K new sizes
     __shared__ double s_est, s_n;
+    __shared__ Stats s_slot[64];
     if (wait_flags != nullptr) {
         // peer-memory exchange: slot s is complete when its flag carries this iteration's epoch.  Bounded spin
         // (~4 s): a missing peer becomes an error code of the call, never a hung GPU.
@@ -299,11 +304,21 @@ __global__ void __launch_bounds__(256) vegas_update_kernel(const double* __restr
         }
         __syncthreads();
     }
+    // slot statistics: loaded by n_slots threads at once, merged in slot order by thread 0
+    if ((int)threadIdx.x < n_slots && threadIdx.x < 64) {
+        const double* ss = slot_stats + (size_t)threadIdx.x * stats_stride;
+        s_slot[threadIdx.x] = Stats{__ldcg(ss), __ldcg(ss + 1), __ldcg(ss + 2)};
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         Stats t{0.0, 0.0, 0.0};
         for (int s = 0; s < n_slots; ++s) {
-            const double* ss = slot_stats + (size_t)s * stats_stride;
-            Stats u{__ldcg(ss), __ldcg(ss + 1), __ldcg(ss + 2)};
+            Stats u;
+            if (s < 64) u = s_slot[s];
+            else {
+                const double* ss = slot_stats + (size_t)s * stats_stride;
+                u = Stats{__ldcg(ss), __ldcg(ss + 1), __ldcg(ss + 2)};
+            }
             t = merge(t, u);
         }
         s_est = t.mean;               // est_j = mean(weighted)           vegas.py:110
