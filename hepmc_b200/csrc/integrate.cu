@@ -583,6 +583,7 @@ int hepmc_vegas_sample(const hepmc_density_t* dens, const double* grid_dev, int 
     a.x_out = x_dev; a.f_out = f_dev; a.w_out = w_dev; a.idx_out = idx_dev;
     a.stats_partials = stats_partials_dev; a.hist_partials = hist_partials_dev;
     a.kpow = pow((double)divisions, (double)ndim);
+    a.kpow_scaled = ldexp(a.kpow, 32 * (ndim > 8 ? ndim - 8 : ndim));
     a.rng_mode = rng_mode;
     a.keys = philox_expand(seed);
     set_camel_centre(a, *dens);

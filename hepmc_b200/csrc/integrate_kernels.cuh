@@ -35,6 +35,7 @@ struct SampleArgs {
     double* stats_partials;
     double* hist_partials;
     double kpow;
+    double kpow_scaled;  // kpow * 2^(32 * (ndim > 8 ? ndim - 8 : ndim)): the scaled-size products of vegas_fast_kernel
     PhiloxKey keys;  // round keys of `seed`, expanded on the host: constant-bank operands of the Philox rounds
     double camel_c, camel_2h, camel_h2;  // centred camel of the throughput kernel (vegas_fast.cuh): (a+b)/2, b-a, n((b-a)/2)^2
     int rng_mode;  // HEPMC_RNG_*: bits per draw and Philox rounds of the native generator (hepmc_set_rng_mode)
@@ -269,6 +270,42 @@ __global__ void __launch_bounds__(256, 1) vegas_sample_kernel(const __grid_const
     }
 }
 
+// A warp's 32 rows of NDIM doubles (one row per lane, in registers) -> global memory in ADDRESS order: the rows go
+// through a skewed shared-memory tile and leave as 512 (256 for odd NDIM) contiguous bytes per store instruction.
+// Rows written straight from registers (one 32-byte piece per lane and instruction, 32 different lines) top out at
+// 4.8 TB/s on B200; warp-contiguous stores reach the copy peak (scripts/store_pattern_bench.cu).
+// tile: 32 * NDIM doubles of this warp; nrows: valid rows (lanes 0 .. nrows-1); dst: address of row 0.
+template <int NDIM>
+__device__ __forceinline__ void warp_store_rows(double* tile, const double (&row)[NDIM], int lane, double* dst, int nrows) {
+    if constexpr (NDIM % 2 == 0) {
+        constexpr int P = NDIM / 2;                       // 16-byte pieces per row
+        double2* t2 = reinterpret_cast<double2*>(tile);
+#pragma unroll
+        for (int j = 0; j < P; ++j) t2[lane * P + (j + lane) % P] = make_double2(row[2 * j], row[2 * j + 1]);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const int idx = j * 32 + lane;
+            const int r = idx / P, c = idx % P;
+            if (r < nrows) {
+                const double2 w = t2[r * P + (c + r) % P];
+                asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(dst + 2 * idx), "d"(w.x), "d"(w.y) : "memory");
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) tile[lane * NDIM + (j + lane) % NDIM] = row[j];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) {
+            const int idx = j * 32 + lane;
+            const int r = idx / NDIM, c = idx % NDIM;
+            if (r < nrows) dst[idx] = tile[r * NDIM + (c + r) % NDIM];
+        }
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------ plain MC
 // NDIM_T: compile-time dimensionality (0 = runtime).  FAST: native RNG only, RNG = its compile-time
 // mode; otherwise replay tapes and the runtime mode a.rng_mode are honoured.
@@ -276,6 +313,8 @@ template <int KIND, int NDIM_T, bool FAST, bool OUT = !FAST, int RNG = HEPMC_RNG
 __global__ void __launch_bounds__(256) plain_sample_kernel(const __grid_constant__ Dens dens,
                                                            const __grid_constant__ SampleArgs a) {
     __shared__ Stats s_stats[8];
+    constexpr bool TILED = OUT && NDIM_T != 0;           // rows leave through warp_store_rows
+    __shared__ double s_tile[TILED ? 8 * 32 * (NDIM_T ? NDIM_T : 1) : 1];
     const int ndim = NDIM_T ? NDIM_T : a.ndim;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr bool fused = KIND != HEPMC_NONE;
@@ -292,7 +331,9 @@ __global__ void __launch_bounds__(256) plain_sample_kernel(const __grid_constant
     acc.init();
     for (int it = 0; it < ppt; ++it) {
         const int64_t li = chunk0 + (int64_t)it * blockDim.x + threadIdx.x;
-        if (li >= a.n) break;
+        // TILED: the warp stays together (its lanes beyond n compute a point nobody stores); else a lane past n is done
+        if (TILED ? (li - lane >= a.n) : (li >= a.n)) break;
+        const bool ok = li < a.n;
         const uint64_t g = (uint64_t)(a.first_index + li);
         PdfAcc pa;
         pa.init();
@@ -330,28 +371,18 @@ __global__ void __launch_bounds__(256) plain_sample_kernel(const __grid_constant
                 }
             }
         }
-        if constexpr (OUT && NDIM_T != 0) {
+        if constexpr (TILED) {
             if (a.x_out) {
-                double* row = a.x_out + li * NDIM_T;
-                if constexpr (NDIM_T % 4 == 0) {
-#pragma unroll
-                    for (int d = 0; d < NDIM_T; d += 4)
-                        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(row + d), "d"(xrow[d]), "d"(xrow[d + 1]),
-                                     "d"(xrow[d + 2]), "d"(xrow[d + 3]) : "memory");
-                } else if constexpr (NDIM_T % 2 == 0) {
-#pragma unroll
-                    for (int d = 0; d < NDIM_T; d += 2) *reinterpret_cast<double2*>(row + d) = make_double2(xrow[d], xrow[d + 1]);
-                } else {
-#pragma unroll
-                    for (int d = 0; d < NDIM_T; ++d) row[d] = xrow[d];
-                }
+                const int64_t w0 = li - lane;                                       // first point of the warp
+                const int nrows = (int)(a.n - w0 < 32 ? a.n - w0 : 32);
+                warp_store_rows<NDIM_T>(s_tile + warp * 32 * NDIM_T, xrow, lane, a.x_out + w0 * NDIM_T, nrows);
             }
         }
         if constexpr (fused) {
             const double f = pdf_acc_finish<KIND>(dens, pa);
-            acc.add(f);
+            if (ok) acc.add(f);
             if constexpr (OUT) {
-                if (a.f_out) a.f_out[li] = f;
+                if (a.f_out && ok) a.f_out[li] = f;
             }
         }
     }

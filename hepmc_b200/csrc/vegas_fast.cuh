@@ -19,6 +19,9 @@
 //     4 instructions per (point, axis): PRMT, LDS, DADD, STS (round 1: 10).
 //   * camel in centred form (3 FP64 instructions per axis instead of 4, see below); the open-cube
 //     test is an integer max over the high words of x (ALU pipe instead of 16 DSETP).
+//   * 32-bit modes, K <= 16: the offset word becomes a double by ONE conversion on the idle XU pipe
+//     (I2F.F64.U32), the 2^-32 scale and the half-quantum shift live in the staged table; the
+//     integrand's exponentials use a 64-entry table of 2^(j/64) + a degree-5 polynomial (Tang's method).
 //   * full chunks run a loop without bounds checks; the shift of the single-pass variance
 //     accumulator is the thread's first value, counts are implied.
 // Determinism: the point -> thread -> lane order is fixed by (chunk, NDIM) only, every sum has
@@ -31,6 +34,12 @@ namespace hepmc {
 
 #ifndef HEPMC_VFAST_MINBLOCKS
 #define HEPMC_VFAST_MINBLOCKS 3
+#endif
+#ifndef HEPMC_VFAST_TABEXP
+#define HEPMC_VFAST_TABEXP 1   // the integrand's exponentials by a 64-entry table of 2^(j/64) + degree-5 polynomial
+#endif
+#ifndef HEPMC_VFAST_I2F
+#define HEPMC_VFAST_I2F 1      // 32-bit modes, K <= 16: offset word -> double by I2F (XU pipe), scaled table (b + s 2^-33, s 2^-32)
 #endif
 template <int NDIM>
 struct HistGeom {
@@ -54,6 +63,8 @@ __host__ __device__ inline size_t vegas_fast_smem_bytes(int ndim, int K, int thr
     b += (size_t)nw * vegas_fast_rows(K) * 32 * 8;   // private histogram columns
     b += (size_t)nw * 32 * 8;                          // f*w tile
     b += (size_t)nw * nq * 36 * 4;                     // packed-bins tile
+    b = (b + 15) & ~(size_t)15;
+    b += 64 * 8;                                       // 2^(j/64) table (HEPMC_VFAST_TABEXP)
     return (b + 15) & ~(size_t)15;
 }
 
@@ -68,6 +79,29 @@ __host__ inline bool camel_uniform_means(const Dens& p) {
         if (p.a[d] != p.a[0] || p.b[d] != p.b[0]) return false;
     return true;
 }
+
+// exp(x) for x <= ~700 by Tang's table method: x = (64 k + j) ln2/64 + r, |r| <= ln2/128;
+// exp(x) = 2^k * T[j] * (1 + r + r^2/2 + ... + r^5/120), T[j] = 2^(j/64) in shared memory; < 1 ulp + table rounding.
+// Valid for |x| < 708 (normal results); callers test exp_tab_ok on the arguments and take the library otherwise.
+__device__ __forceinline__ double exp_tab(double x, const double* tab64) {
+    const double MAGIC = 6755399441055744.0;                       // 1.5 * 2^52
+    const double t = fma(x, 92.332482616893657, MAGIC);            // 64 / ln 2
+    const int n = __double2loint(t);
+    const double nd = t - MAGIC;
+    double r = fma(nd, -0.01083042469326756, x);                // ln2/64, top 32 mantissa bits (nd * hi is exact)
+    r = fma(nd, -2.9815858269852933e-12, r);                       // ln2/64 - hi
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(r, p, 1.0 / 6.0);
+    p = fma(r, p, 0.5);
+    p = fma(r * r, p, r);                                          // e^r - 1
+    const double tj = tab64[n & 63];
+    const double v = fma(tj, p, tj);
+    const int k = n >> 6;
+    return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
+}
+
+// |x| < 708 (false for NaN and inf): one mask and one integer compare on the high word
+__device__ __forceinline__ bool exp_tab_ok(double x) { return (__double2hiint(x) & 0x7fffffff) < 0x40862000; }
 
 // KP: compile-time grid row stride (16) or 0 = runtime stride K
 template <int KIND, int NDIM, int RNG, bool OUT, int KP>
@@ -91,18 +125,31 @@ __global__ void __launch_bounds__(256, OUT ? 2 : HEPMC_VFAST_MINBLOCKS) vegas_fa
     double* s_hist = reinterpret_cast<double*>(s_stats + 8);                       // [nw][RW][32]
     double* s_wf = s_hist + (size_t)nw * RW * 32;                           // [nw][32]
     uint32_t* s_bins = reinterpret_cast<uint32_t*>(s_wf + nw * 32);                // [nw][NQ][36]
+    double* s_exp = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_bins + nw * NQ * G::ROW) + 15) & ~(uintptr_t)15);
+    constexpr bool TABEXP = HEPMC_VFAST_TABEXP && (camel || KIND == HEPMC_BANANA || KIND == HEPMC_GAUSSIAN);
+    if constexpr (TABEXP) {
+        if (threadIdx.x < 64) s_exp[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / 64.0));
+    }
 
     constexpr bool W32 = RNG != HEPMC_RNG_U52_R10;
     // K <= 16: bounds and sizes as separate rows of 16 doubles (128 B: every entry in its own bank pair, so
     // the random-bin look-ups of a half-warp never conflict); else (bound, size) pairs, one LDS.128
     constexpr bool SOA = KP == 16;
+    // 32-bit modes on the SoA layout: x = b + s (lo + 1/2) 2^-32 = (b + s 2^-33) + (s 2^-32) lo.  The table holds
+    // b2 = b + s 2^-33 (one rounding, <= ulp(b)/2) and s32 = s 2^-32 (exact); the offset word becomes a double with ONE
+    // conversion instruction on the otherwise idle XU pipe (I2F.F64.U32) instead of building the (lo, 0x41300000)
+    // register pair (2 moves) and subtracting: 2 issue slots and 1 FP64 instruction less per axis.  The weight
+    // prod(s) is taken from s32 as well and rescaled by exact powers of two (2^256 after 8 axes, the rest with K^n).
+    constexpr bool I2F = HEPMC_VFAST_I2F && SOA && W32;
     double* s_gb = reinterpret_cast<double*>(s_grid2);
     double* s_gs = s_gb + (size_t)NDIM * KS;
     for (int i = threadIdx.x; i < NDIM * K; i += 256) {
         const int d = i / K, k = i - d * K;
         const double* gd = a.grid + d * (2 * K + 1);
-        if constexpr (SOA) { s_gb[d * KS + k] = gd[k]; s_gs[d * KS + k] = gd[K + 1 + k]; }
-        else s_grid2[d * KS + k] = make_double2(gd[k], gd[K + 1 + k]);
+        const double gbv = gd[k], gsv = gd[K + 1 + k];
+        if constexpr (I2F) { s_gb[d * KS + k] = fma(gsv, 0x1p-33, gbv); s_gs[d * KS + k] = gsv * 0x1p-32; }
+        else if constexpr (SOA) { s_gb[d * KS + k] = gbv; s_gs[d * KS + k] = gsv; }
+        else s_grid2[d * KS + k] = make_double2(gbv, gsv);
     }
     if constexpr (fused)
         for (int i = threadIdx.x; i < nw * RW * 32; i += 256) s_hist[i] = 0.0;
@@ -183,13 +230,20 @@ __global__ void __launch_bounds__(256, OUT ? 2 : HEPMC_VFAST_MINBLOCKS) vegas_fa
                     if (d < NDIM) {
                         uint32_t bin;
                         double frac;
-                        if constexpr (W32) bin_frac32(rw[h], (uint32_t)K, bin, frac);
+                        if constexpr (I2F) {
+                            const uint64_t t = (uint64_t)(uint32_t)K * rw[h];
+                            bin = (uint32_t)(t >> 32);
+                            frac = __uint2double_rn((uint32_t)t);            // (t mod 2^32) as a double; scaling lives in the table
+                        } else if constexpr (W32) bin_frac32(rw[h], (uint32_t)K, bin, frac);
                         else bin_frac(rw[2 * h], rw[2 * h + 1], (uint32_t)K, bin, frac);
                         double gb, gs;
                         if constexpr (SOA) { gb = s_gb[d * KS + bin]; gs = s_gs[d * KS + bin]; }
                         else { const double2 bs = s_grid2[d * KS + bin]; gb = bs.x; gs = bs.y; }
                         const double x = fma(gs, frac, gb);      // stratified_volume.py:119-121
                         w *= gs;                                 // vegas.py:69-70
+                        if constexpr (I2F && NDIM > 8) {
+                            if (d == 7) w *= 0x1p+256;           // exact: keeps the partial product of scaled sizes in range
+                        }
                         if constexpr (camel) {
                             const double tc = x - a.camel_c;
                             pa.m0 += tc;                         // S1
@@ -208,7 +262,9 @@ __global__ void __launch_bounds__(256, OUT ? 2 : HEPMC_VFAST_MINBLOCKS) vegas_fa
                     }
                 }
             }
-            w *= a.kpow;  // vegas.py:72 (partition_count in floating point, App. B1)
+            // vegas.py:72 (partition_count in floating point, App. B1); I2F: times the remaining power of two
+            if constexpr (I2F) w *= a.kpow_scaled;
+            else w *= a.kpow;
             if constexpr (OUT) {
                 if (a.w_out && ok) a.w_out[li] = w;
             }
@@ -219,7 +275,19 @@ __global__ void __launch_bounds__(256, OUT ? 2 : HEPMC_VFAST_MINBLOCKS) vegas_fa
                     pa.m0 = base + cross;
                     pa.m1 = base - cross;
                 }
-                const double f = pdf_acc_finish<KIND>(dens, pa);
+                double f;
+                if constexpr (TABEXP && camel) {
+                    const double s2 = dens.s0 * dens.s0;             // camel.py:31 with the table exponential
+                    const double ea = -0.5 * (dens.s1 + s2 * pa.m0), eb = -0.5 * (dens.s1 + s2 * pa.m1);
+                    if (__builtin_expect(exp_tab_ok(ea) && exp_tab_ok(eb), 1)) f = (exp_tab(ea, s_exp) + exp_tab(eb, s_exp)) / 2.0;
+                    else f = (exp(ea) + exp(eb)) / 2.0;              // subnormal / zero / overflowing terms: the library
+                    if (KIND == HEPMC_CAMEL && !pa.inside) f = 0.0;
+                } else if constexpr (TABEXP) {
+                    const double ea = -0.5 * (dens.s1 + pa.m0);      // banana.py / gaussian.py: exp(logpdf)
+                    f = __builtin_expect(exp_tab_ok(ea), 1) ? exp_tab(ea, s_exp) : exp(ea);
+                } else {
+                    f = pdf_acc_finish<KIND>(dens, pa);
+                }
                 double wf = f * w;  // vegas.py:104
                 if constexpr (OUT) {
                     if (a.f_out && ok) a.f_out[li] = f;

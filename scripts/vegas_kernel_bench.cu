@@ -75,6 +75,7 @@ int main(int argc, char** argv) {
     SampleArgs a{};
     a.grid = g_dev; a.ndim = ndim; a.K = K; a.n = n; a.first_index = 0; a.chunk = chunk; a.seed = 1234;
     a.kpow = pow((double)K, (double)ndim);
+    a.kpow_scaled = ldexp(a.kpow, 32 * (ndim > 8 ? ndim - 8 : ndim));
     a.keys = philox_expand(a.seed);
     set_camel_centre(a, dens);
     cudaMalloc(&a.stats_partials, (size_t)blocks * 3 * 8);
