@@ -27,6 +27,13 @@ class MetropolisUpdate(MarkovUpdate):
 
 
 class DefaultMetropolis(MetropolisUpdate):
+    """Metropolis(-Hastings) update with a `Proposal` (metropolis.py:98-127).
+
+    Native draws of the ensemble kernel (symmetric proposals over a built-in target): the accept uniform of a
+    step is taken from the 24 bits the step's proposal draw leaves unused, u = (k + 1/2) 2^-24.  The realised
+    acceptance probability is therefore the Metropolis ratio rounded to a multiple of 2^-24 (absolute error
+    <= 3e-8 per step), and a move with ratio < 3e-8 is never accepted.  `HamiltonianUpdate` and the (MC)^3
+    mixing kernel draw a full 52-bit accept uniform; replay tapes are used as given."""
 
     def __init__(self, ndim, target, proposal=None, adaptive=False):
         if proposal is None:

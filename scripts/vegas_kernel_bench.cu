@@ -53,6 +53,37 @@ static void run(const char* tag, const Dens& dens, SampleArgs a, int blocks, siz
            (double)a.n / (sum / reps * 1e-3), fa.numRegs, nb, cn, cs, ch);
 }
 
+template <int RNG>
+static void run_out(const char* tag, const Dens& dens, SampleArgs a, size_t smem, int reps) {
+    // keep_samples = True: x (ndim, n) dim-major, f (n), w (n) written: 8 (ndim + 2) bytes per point
+    const int64_t n = 100000000LL;
+    a.n = n;
+    const int blocks = (int)((n + a.chunk - 1) / a.chunk);
+    check_cuda(cudaMalloc(&a.x_out, (size_t)n * BENCH_NDIM * 8), "x");
+    check_cuda(cudaMalloc(&a.f_out, (size_t)n * 8), "f");
+    check_cuda(cudaMalloc(&a.w_out, (size_t)n * 8), "w");
+    auto kern = vegas_fast_kernel<HEPMC_CAMEL, BENCH_NDIM, RNG, true, 16>;
+    check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr");
+    check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100), "attr2");
+    a.rng_mode = RNG;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float sum = 0.f;
+    for (int i = 0; i < reps + 2; ++i) {
+        a.stream_id = 300 + i;
+        cudaEventRecord(e0);
+        kern<<<blocks, 256, smem>>>(dens, a);
+        cudaEventRecord(e1);
+        check_cuda(cudaEventSynchronize(e1), "sync");
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (i >= 2) sum += ms;
+    }
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
+    int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, smem);
+    printf("%-8s keep: %.3f ms  %.4g pts/s  %.0f GB/s written  regs %d blocks/SM %d\n", tag, sum / reps, (double)n / (sum / reps * 1e-3),
+           (double)n * 8 * (BENCH_NDIM + 2) / (sum / reps * 1e-3) / 1e9, fa.numRegs, nb);
+    cudaFree(a.x_out); cudaFree(a.f_out); cudaFree(a.w_out);
+}
+
 int main(int argc, char** argv) {
     const int64_t n = argc > 1 ? (int64_t)atof(argv[1]) : 1000000000LL;
     const int K = 15, ndim = BENCH_NDIM;
@@ -85,5 +116,6 @@ int main(int argc, char** argv) {
     run<0>("u52r10", dens, a, blocks, smem, 4);
     run<1>("u32r10", dens, a, blocks, smem, 4);
     run<2>("u32r7", dens, a, blocks, smem, 4);
+    run_out<1>("u32r10", dens, a, smem, 4);
     return 0;
 }

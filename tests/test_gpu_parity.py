@@ -525,8 +525,7 @@ def test_uniform_local_metropolis():
     w = O.philox_words(77, 0, 7 + np.arange(C), 2 * (T - 1)).astype(np.uint32)
     vv = O.u52(w[:, 0::2, 0], w[:, 0::2, 1])
     uu = O.u24_spare(w[:, 0::2, 0], w[:, 0::2, 2])
-    ur = O.u52(w[:, 1::2, 0], w[:, 1::2, 1])                 # ratios < 2^-12: full uniform of the step's second call
-    chain, acc = O.uniform_local_chains(O.camel_pdf, x0, vv, uu, delta, u_rare=ur)
+    chain, acc = O.uniform_local_chains(O.camel_pdf, x0, vv, uu, delta)
     assert np.array_equal(s.accepted, acc)
     assert_close(s.data, chain, 1e-12, atol=1e-15)
     assert s.data.min() >= 0.0 and s.data.max() <= 1.0       # the box is pushed back into [0, 1]
@@ -548,13 +547,11 @@ def test_metropolis_native_matches_oracle_draws():
     w = O.philox_words(31337, 0, idx, 2 * (T - 1)).astype(np.uint32)
     z = np.empty((C, T - 1, 2))
     u = np.empty((C, T - 1))
-    u_rare = np.empty((C, T - 1))
     for t in range(T - 1):
         z0, z1 = O.box_muller(O.u52(w[:, 2 * t, 0], w[:, 2 * t, 1]), O.u52(w[:, 2 * t, 2], w[:, 2 * t, 3]))
         z[:, t, 0], z[:, t, 1] = z0, z1
         u[:, t] = O.u24_spare(w[:, 2 * t, 0], w[:, 2 * t, 2])
-        u_rare[:, t] = O.u52(w[:, 2 * t + 1, 0], w[:, 2 * t + 1, 1])    # ratios < 2^-12: the step's second call
-    chain, acc = O.metropolis_chains(O.banana_pdf, x0, z, u, np.sqrt([10., 10.]), u_rare=u_rare)
+    chain, acc = O.metropolis_chains(O.banana_pdf, x0, z, u, np.sqrt([10., 10.]))
     assert np.array_equal(s.accepted, acc)
     assert_close(s.data, chain, 1e-10, atol=1e-10)
 
@@ -1166,8 +1163,7 @@ def test_edge_cases_maximum_sizes():
             z0, z1 = O.box_muller(O.u52(w[:, 9 * t + k, 0], w[:, 9 * t + k, 1]), O.u52(w[:, 9 * t + k, 2], w[:, 9 * t + k, 3]))
             z[:, t, 2 * k], z[:, t, 2 * k + 1] = z0, z1
         u[:, t] = O.u24_spare(w[:, 9 * t, 0], w[:, 9 * t, 2])      # spare bits of the step's first proposal call
-    ur = O.u52(w[:, 8::9, 0], w[:, 8::9, 1])                       # ratios < 2^-12: the step's ninth call
-    chain, acc = O.metropolis_chains(lambda x: O.gaussian_pdf(x, 0.5, 0.01), x0, z, u, np.full(nd, 0.02), u_rare=ur)
+    chain, acc = O.metropolis_chains(lambda x: O.gaussian_pdf(x, 0.5, 0.01), x0, z, u, np.full(nd, 0.02))
     assert np.array_equal(s.accepted, acc)
     assert_close(s.data, chain, 1e-10, atol=1e-12)
     with pytest.raises(RuntimeError):
