@@ -7,6 +7,7 @@
 // the same chains.  Acceptance counts: per chain + warp-shuffle reduced grid total.
 #include <stdlib.h>
 #include "chains.cuh"
+#include "tabmath.cuh"
 
 namespace hepmc {
 
@@ -15,6 +16,15 @@ namespace hepmc {
 template <int NDIM>
 __global__ void __launch_bounds__(128) rwm_kernel(const __grid_constant__ Dens dens,
                                                   const __grid_constant__ ChainArgs a) {
+    // Box-Muller and the target's exponential through the table-driven functions of tabmath.cuh (built once per
+    // CTA, used T times per thread): 412 -> ~350 instructions per step
+    __shared__ tm::Tables tabs;
+    tm::build(tabs);
+    struct TabExp {
+        const tm::Tables& t;
+        __device__ __forceinline__ double operator()(double v) const { return tm::exp(v, t); }
+    };
+    const TabExp texp{tabs};
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = c < a.n_chains;
     const PhiloxKey key = philox_expand(a.seed);
@@ -26,7 +36,7 @@ __global__ void __launch_bounds__(128) rwm_kernel(const __grid_constant__ Dens d
         double x[NDIM];
 #pragma unroll
         for (int d = 0; d < NDIM; ++d) x[d] = a.x0[c * NDIM + d];
-        double pdf = density_pdf_n<NDIM>(dens, x);  // init_state, metropolis.py:68-74
+        double pdf = density_pdf_n<NDIM>(dens, x, texp);  // init_state, metropolis.py:68-74
         if (a.chain) store_state<NDIM>(a.chain, c, a.n_kept, 0, x);
         for (int64_t t = 1; t < a.T; ++t) {
             double cand[NDIM];
@@ -44,7 +54,13 @@ __global__ void __launch_bounds__(128) rwm_kernel(const __grid_constant__ Dens d
                     if (k == 0) u_spare = u24_spare(r.x, r.z);
                     double z0, z1;
                     if (a.prop_kind == 0) {
-                        normal_pair(r, z0, z1);
+                        // Box-Muller on two 52-bit uniforms (same convention as normal_pair, table-driven functions)
+                        const double u1 = u52(r.x, r.y), u2 = u52(r.z, r.w);
+                        const double rad = sqrt(-2.0 * tm::log(u1, tabs));
+                        double sn, cs;
+                        tm::sincos2pi_post(tm::sincos2pi_pre(u2, tabs), sn, cs);
+                        z0 = rad * cs;
+                        z1 = rad * sn;
                     } else {
                         z0 = u52(r.x, r.y);
                         z1 = u52(r.z, r.w);
@@ -67,7 +83,7 @@ __global__ void __launch_bounds__(128) rwm_kernel(const __grid_constant__ Dens d
                     cand[d] = a.prop_kind == 0 ? x[d] + a.scale[d] * z[d]            // proposals/gaussian.py:25-27
                                                : a.prop_lo + (a.prop_hi - a.prop_lo) * z[d];  // uniform.py:33-34
             }
-            const double cpdf = density_pdf_n<NDIM>(dens, cand);
+            const double cpdf = density_pdf_n<NDIM>(dens, cand, texp);
             const double ratio = cpdf / pdf;  // metropolis.py:50
             // native mode: the accept uniform comes from the spare bits of the proposal draw (common.cuh): 24 bits,
             // (k + 1/2) 2^-24.  The realised acceptance probability is the ratio rounded to a multiple of 2^-24 and

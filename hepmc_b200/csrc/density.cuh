@@ -47,14 +47,19 @@ __device__ __forceinline__ void pdf_acc_dim(const Dens& p, PdfAcc& acc, int d, d
     }
 }
 
-template <int KIND>
-__device__ __forceinline__ double pdf_acc_finish(const Dens& p, const PdfAcc& acc) {
+// EXP: the exponential to use -- the library's (default) or a table-driven one (tabmath.cuh) in throughput kernels
+struct LibExp {
+    __device__ __forceinline__ double operator()(double x) const { return exp(x); }
+};
+
+template <int KIND, class EXP = LibExp>
+__device__ __forceinline__ double pdf_acc_finish(const Dens& p, const PdfAcc& acc, const EXP& ex = EXP()) {
     if constexpr (KIND == HEPMC_CAMEL || KIND == HEPMC_UCAMEL) {
         if (KIND == HEPMC_CAMEL && !acc.inside) return 0.0;
         const double s2 = p.s0 * p.s0;  // (sqrt(1/cov))^2
-        return (exp(-0.5 * (p.s1 + s2 * acc.m0)) + exp(-0.5 * (p.s1 + s2 * acc.m1))) / 2.0;  // camel.py:31
+        return (ex(-0.5 * (p.s1 + s2 * acc.m0)) + ex(-0.5 * (p.s1 + s2 * acc.m1))) / 2.0;  // camel.py:31
     } else if constexpr (KIND == HEPMC_BANANA || KIND == HEPMC_GAUSSIAN) {
-        return exp(-0.5 * (p.s1 + acc.m0));
+        return ex(-0.5 * (p.s1 + acc.m0));
     } else if constexpr (KIND == HEPMC_UNIFORM) {
         return acc.inside ? 1.0 / p.s2 : 0.0;
     } else {
@@ -81,13 +86,13 @@ __device__ __forceinline__ double pdf_k(const Dens& p, const X& x, int ndim) {
     return pdf_acc_finish<KIND>(p, acc);
 }
 
-template <int KIND, int NDIM, class X>
-__device__ __forceinline__ double pdf_kn(const Dens& p, const X& x) {
+template <int KIND, int NDIM, class X, class EXP = LibExp>
+__device__ __forceinline__ double pdf_kn(const Dens& p, const X& x, const EXP& ex = EXP()) {
     PdfAcc acc;
     acc.init();
 #pragma unroll
     for (int d = 0; d < NDIM; ++d) pdf_acc_dim<KIND>(p, acc, d, x[d]);
-    return pdf_acc_finish<KIND>(p, acc);
+    return pdf_acc_finish<KIND, EXP>(p, acc, ex);
 }
 
 // runtime-kind wrappers: ONE dispatch per point, loops inside the case
@@ -98,10 +103,10 @@ __device__ __forceinline__ double density_pdf(const Dens& p, const X& x) {
     return r;
 }
 
-template <int NDIM, class X>
-__device__ __forceinline__ double density_pdf_n(const Dens& p, const X& x) {
+template <int NDIM, class X, class EXP = LibExp>
+__device__ __forceinline__ double density_pdf_n(const Dens& p, const X& x, const EXP& ex = EXP()) {
     double r = 0.0;
-    HEPMC_KIND_SWITCH(p.kind, r = (pdf_kn<KIND, NDIM>(p, x)));
+    HEPMC_KIND_SWITCH(p.kind, r = (pdf_kn<KIND, NDIM, X, EXP>(p, x, ex)));
     return r;
 }
 

@@ -9,14 +9,14 @@
 // division inside the log), 320 Philox.  Native mode now
 //   * draws in the integrators' RNG modes (hepmc_rng_mode): in the 32-bit modes one Philox call per
 //     particle (u0..u3 = its four words) instead of two;
-//   * -log(u2 u3) by a 128-entry table of (1/c_j, log c_j) in shared memory: r = m/c_j - 1,
-//     |r| <= 2^-8, degree-6 log1p (no division; abs. error < 2e-16);
-//   * (sin, cos)(2 pi u1) by a 64-entry table of (cos, sin)(2 pi k/64) and degree-7/8 polynomials
-//     on |x| <= pi/64 plus one rotation (abs. error < 2e-16).
+//   * -log(u2 u3) and (sin, cos)(2 pi u1) by the table-driven functions of tabmath.cuh (128-entry table of
+//     (1/c_j, log c_j) + degree-6 log1p, no division; 64-entry table of (cos, sin)(2 pi k/64) + degree-7/8
+//     polynomials + one rotation; abs. errors < 2e-16);
 // The tables are built by the CTA itself with the library functions (grid-stride CTAs: amortised over
 // hundreds of points per thread).  Replay mode (the reference's own uniforms) uses the same arithmetic:
 // parity with the reference is 1e-12 either way (tests/test_gpu_parity.py::test_rambo_replay).
 #include "integrate_kernels.cuh"
+#include "tabmath.cuh"
 
 namespace hepmc {
 
@@ -38,78 +38,25 @@ __device__ __forceinline__ void ld256(const double* p, double& a, double& b, dou
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
-constexpr int kLogTab = 128, kTrigTab = 64;
-
-// tab_log[j] = (1/c_j, log c_j), c_j = 1 + (j + 1/2)/128;  tab_trig[k] = (cos, sin)(2 pi k / 64)
-__device__ __forceinline__ void rambo_build_tables(double2* tab_log, double2* tab_trig) {
-    for (int j = threadIdx.x; j < kLogTab; j += blockDim.x) {
-        const double c = 1.0 + (j + 0.5) * (1.0 / kLogTab);
-        tab_log[j] = make_double2(1.0 / c, ::log(c));
-    }
-    for (int k = threadIdx.x; k < kTrigTab; k += blockDim.x) {
-        double sn, cs;
-        sincospi((double)k * (2.0 / kTrigTab), &sn, &cs);
-        tab_trig[k] = make_double2(cs, sn);
-    }
-    __syncthreads();
-}
-
-// polynomial and scaling constants in the constant bank: used directly as DFMA / DMUL operands (64-bit
-// literals would be re-materialised with UMOV pairs at every use: 72 of 766 instructions per point)
-static __constant__ double kR[16] = {
-    -1.0 / 6.0, 0.2, 1.0 / 3.0,                       // 0..2  log1p
-    0.6931471803691238, 1.9082149292705877e-10,       // 3,4   ln2 hi, lo
-    6755399441055744.0,                               // 5     1.5 * 2^52
-    6.283185307179586 / kTrigTab,                     // 6     2 pi / 64
-    -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0,           // 7..9  sin
-    1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0,          // 10..12 cos
-    (double)kTrigTab, 0.0, 0.0};
-
 // map_fourvector_rambo, rambo.py:162-173, in two stages so that the table look-ups of all particles of a
 // point are in flight before the first polynomial starts (the look-up latency was 28 % of the stall samples):
 // stage 1: indices, reduced arguments and the two table entries; stage 2: polynomials, rotation, q.
 struct RamboPre {
-    double c;        // cos theta = 2 u0 - 1
-    double x;        // reduced angle, |x| <= pi/64
-    double m, ed;    // mantissa in [1,2) and exponent of u2 u3
-    double2 tl, tt;  // (1/c_j, log c_j), (cos, sin) of the table angle
+    double c;            // cos theta = 2 u0 - 1
+    tm::TrigPre trig;    // phi = 2 pi u1
+    tm::LogPre lg;       // log(u2 u3)
 };
 
-__device__ __forceinline__ void rambo_stage1(double u0, double u1, double u2, double u3, const double2* tab_log,
-                                             const double2* tab_trig, RamboPre& r) {
+__device__ __forceinline__ void rambo_stage1(double u0, double u1, double u2, double u3, const tm::Tables& tb, RamboPre& r) {
     r.c = fma(2.0, u0, -1.0);
-    const double tk = fma(u1, kR[13], kR[5]);
-    const int k = __double2loint(tk);                           // nearest multiple of 1/64: 0 .. 64
-    const double f = fma(u1, kR[13], -(tk - kR[5]));            // in [-1/2, 1/2], exact
-    r.x = f * kR[6];
-    r.tt = tab_trig[k & (kTrigTab - 1)];
-    const double prod = u2 * u3;                                // normal: >= 2^-106
-    const int hi = __double2hiint(prod);
-    r.ed = (double)((hi >> 20) - 1023);
-    r.m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(prod));   // [1, 2)
-    r.tl = tab_log[(hi >> 13) & (kLogTab - 1)];
+    r.trig = tm::sincos2pi_pre(u1, tb);
+    r.lg = tm::log_pre(u2 * u3, tb);                            // normal: >= 2^-106
 }
 
 __device__ __forceinline__ void rambo_stage2(const RamboPre& r, double q[4]) {
-    // -log(u2 u3) = -(e ln2 + log c_j + log1p(m / c_j - 1)), |m / c_j - 1| <= 2^-8: degree 6, abs. error < 2e-16
-    const double t = fma(r.m, r.tl.x, -1.0);
-    double p = fma(t, kR[0], kR[1]);
-    p = fma(t, p, -0.25);
-    p = fma(t, p, kR[2]);
-    p = fma(t, p, -0.5);
-    p = fma(t * t, p, t);
-    const double q0 = -(fma(r.ed, kR[3], r.tl.y) + fma(r.ed, kR[4], p));
-    // (sin, cos)(2 pi u1) = rotation of the table angle by x
-    const double x2 = r.x * r.x;
-    double ps = fma(x2, kR[7], kR[8]);
-    ps = fma(x2, ps, kR[9]);
-    const double s = fma(r.x * x2, ps, r.x);
-    double pc = fma(x2, kR[10], kR[11]);
-    pc = fma(x2, pc, kR[12]);
-    pc = fma(x2, pc, -0.5);
-    const double c = fma(x2, pc, 1.0);
-    const double sn = fma(r.tt.y, c, r.tt.x * s);
-    const double cs = fma(r.tt.x, c, -(r.tt.y * s));
+    const double q0 = -tm::log_post(r.lg);
+    double sn, cs;
+    tm::sincos2pi_post(r.trig, sn, cs);
     // 1 - c*c with the reference's two roundings (rambo.py:166): near c = +-1 the rounding of c*c IS the
     // value; a fused multiply-add would be more accurate and differ from the reference by up to 1e-11
     const double st = q0 * sqrt(1.0 - r.c * r.c);
@@ -119,10 +66,9 @@ __device__ __forceinline__ void rambo_stage2(const RamboPre& r, double q[4]) {
     q[3] = q0 * r.c;
 }
 
-__device__ __forceinline__ void rambo_q(double u0, double u1, double u2, double u3, const double2* tab_log,
-                                        const double2* tab_trig, double q[4]) {
+__device__ __forceinline__ void rambo_q(double u0, double u1, double u2, double u3, const tm::Tables& tb, double q[4]) {
     RamboPre r;
-    rambo_stage1(u0, u1, u2, u3, tab_log, tab_trig, r);
+    rambo_stage1(u0, u1, u2, u3, tb, r);
     rambo_stage2(r, q);
 }
 
@@ -170,10 +116,9 @@ __device__ __forceinline__ void rambo_draw(uint64_t g, int p, uint32_t stream_id
 template <int NP, int RNG, bool REPLAY>
 __global__ void __launch_bounds__(128, HEPMC_RAMBO_MINBLOCKS) rambo_kernel(const __grid_constant__ RamboArgs a) {
     constexpr int P = 2 * NP;                      // 16-byte pieces per point
-    __shared__ double2 tab_log[kLogTab];
-    __shared__ double2 tab_trig[kTrigTab];
+    __shared__ tm::Tables tabs;
     __shared__ double2 tile[4][32 * P];
-    rambo_build_tables(tab_log, tab_trig);
+    tm::build(tabs, false);
     const PhiloxKey& key = a.keys;
     const double e_cm = a.e_cm;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -195,7 +140,7 @@ __global__ void __launch_bounds__(128, HEPMC_RAMBO_MINBLOCKS) rambo_kernel(const
                         double u0, u1, u2, u3;
                         if constexpr (REPLAY) ld256(a.xs + (i * NP + p) * 4, u0, u1, u2, u3);
                         else rambo_draw<RNG>(g, p, a.stream_id, key, u0, u1, u2, u3);
-                        rambo_stage1(u0, u1, u2, u3, tab_log, tab_trig, pre[j]);
+                        rambo_stage1(u0, u1, u2, u3, tabs, pre[j]);
                     }
                 }
 #pragma unroll
@@ -239,9 +184,8 @@ __global__ void __launch_bounds__(128, HEPMC_RAMBO_MINBLOCKS) rambo_kernel(const
 
 // any particle count: q parked in the output row (same thread re-reads what it wrote)
 __global__ void __launch_bounds__(128) rambo_kernel_generic(const __grid_constant__ RamboArgs a, int np) {
-    __shared__ double2 tab_log[kLogTab];
-    __shared__ double2 tab_trig[kTrigTab];
-    rambo_build_tables(tab_log, tab_trig);
+    __shared__ tm::Tables tabs;
+    tm::build(tabs, false);
     const PhiloxKey& key = a.keys;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -253,7 +197,7 @@ __global__ void __launch_bounds__(128) rambo_kernel_generic(const __grid_constan
             else if (a.rng_mode == HEPMC_RNG_U52_R10) rambo_draw<HEPMC_RNG_U52_R10>(g, p, a.stream_id, key, u0, u1, u2, u3);
             else if (a.rng_mode == HEPMC_RNG_U32_R10) rambo_draw<HEPMC_RNG_U32_R10>(g, p, a.stream_id, key, u0, u1, u2, u3);
             else rambo_draw<HEPMC_RNG_U32_R7>(g, p, a.stream_id, key, u0, u1, u2, u3);
-            rambo_q(u0, u1, u2, u3, tab_log, tab_trig, q);
+            rambo_q(u0, u1, u2, u3, tabs, q);
             Q0 += q[0]; Q1 += q[1]; Q2 += q[2]; Q3 += q[3];
             st256(a.out + (i * np + p) * 4, q[0], q[1], q[2], q[3]);
         }

@@ -66,8 +66,8 @@ __host__ __device__ inline size_t vegas_fast_smem_bytes(int ndim, int K, int thr
     b += (size_t)nw * vegas_fast_rows(K) * 32 * 8;   // private histogram columns
     b += (size_t)nw * 32 * 8;                          // f*w tile
     b += (size_t)nw * nq * 36 * 4;                     // packed-bins tile
-    b = (b + 15) & ~(size_t)15;
-    b += 64 * 8;                                       // 2^(j/64) table (HEPMC_VFAST_TABEXP)
+    b = (b + 127) & ~(size_t)127;                      // 128-byte aligned: one bank row for the 16-entry table
+    b += 64 * 8;                                       // 2^(j/T) table of the exponentials (up to 64 entries)
     return (b + 15) & ~(size_t)15;
 }
 
@@ -83,23 +83,39 @@ __host__ inline bool camel_uniform_means(const Dens& p) {
     return true;
 }
 
-// exp(x) for x <= ~700 by Tang's table method: x = (64 k + j) ln2/64 + r, |r| <= ln2/128;
-// exp(x) = 2^k * T[j] * (1 + r + r^2/2 + ... + r^5/120), T[j] = 2^(j/64) in shared memory; < 1 ulp + table rounding.
+#ifndef HEPMC_VFAST_EXPTAB_BITS
+#define HEPMC_VFAST_EXPTAB_BITS 6      // 64 entries; 16 (one conflict-free 128-byte row, degree-7 polynomial) measured the same
+#endif
+constexpr int kExpBits = HEPMC_VFAST_EXPTAB_BITS;
+constexpr int kExpTab = 1 << kExpBits;
+
+// exp(x) by Tang's table method: x = (T k + j) ln2/T + r, |r| <= ln2/(2T); exp(x) = 2^k * tab[j] * e^r,
+// tab[j] = 2^(j/T) in shared memory.  T = 16: degree-7 polynomial (r^8/8! < 2e-18); T = 64: degree 5.
 // Valid for |x| < 708 (normal results); callers test exp_tab_ok on the arguments and take the library otherwise.
-__device__ __forceinline__ double exp_tab(double x, const double* tab64) {
+__device__ __forceinline__ double exp_tab(double x, const double* tab) {
     const double MAGIC = 6755399441055744.0;                       // 1.5 * 2^52
-    const double t = fma(x, 92.332482616893657, MAGIC);            // 64 / ln 2
+    constexpr double INV = kExpBits == 4 ? 23.083120654223414 : 92.332482616893657;          // T / ln 2
+    constexpr double HI = kExpBits == 4 ? 0.04332169877307024 : 0.01083042469326756;         // ln2/T, top 32 mantissa bits
+    constexpr double LO = kExpBits == 4 ? 1.1926343307941173e-11 : 2.9815858269852933e-12;   // ln2/T - HI
+    const double t = fma(x, INV, MAGIC);
     const int n = __double2loint(t);
     const double nd = t - MAGIC;
-    double r = fma(nd, -0.01083042469326756, x);                // ln2/64, top 32 mantissa bits (nd * hi is exact)
-    r = fma(nd, -2.9815858269852933e-12, r);                       // ln2/64 - hi
-    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    double r = fma(nd, -HI, x);                                    // nd * HI is exact
+    r = fma(nd, -LO, r);
+    double p;
+    if constexpr (kExpBits == 4) {
+        p = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
+        p = fma(r, p, 1.0 / 120.0);
+        p = fma(r, p, 1.0 / 24.0);
+    } else {
+        p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    }
     p = fma(r, p, 1.0 / 6.0);
     p = fma(r, p, 0.5);
     p = fma(r * r, p, r);                                          // e^r - 1
-    const double tj = tab64[n & 63];
+    const double tj = tab[n & (kExpTab - 1)];
     const double v = fma(tj, p, tj);
-    const int k = n >> 6;
+    const int k = n >> kExpBits;
     return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
 }
 
@@ -128,10 +144,10 @@ __global__ void __launch_bounds__(256, OUT ? HEPMC_VFAST_OUT_MINBLOCKS : HEPMC_V
     double* s_hist = reinterpret_cast<double*>(s_stats + 8);                       // [nw][RW][32]
     double* s_wf = s_hist + (size_t)nw * RW * 32;                           // [nw][32]
     uint32_t* s_bins = reinterpret_cast<uint32_t*>(s_wf + nw * 32);                // [nw][NQ][36]
-    double* s_exp = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_bins + nw * NQ * G::ROW) + 15) & ~(uintptr_t)15);
+    double* s_exp = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_bins + nw * NQ * G::ROW) + 127) & ~(uintptr_t)127);
     constexpr bool TABEXP = HEPMC_VFAST_TABEXP && (camel || KIND == HEPMC_BANANA || KIND == HEPMC_GAUSSIAN);
     if constexpr (TABEXP) {
-        if (threadIdx.x < 64) s_exp[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / 64.0));
+        if (threadIdx.x < kExpTab) s_exp[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / kExpTab));
     }
 
     constexpr bool W32 = RNG != HEPMC_RNG_U52_R10;
