@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(256) vegas_accumulate_kernel(const __grid_cons
     }
     __syncthreads();
     block_hist_flush(s.hist, ndim, K, nw, a.hist_partials + (size_t)blockIdx.x * ndim * K);
-    Stats st = warp_merge(acc.stats());
+    // full chunk: equal counts in every lane -> the division-free butterfly (same bits, common.cuh)
+    Stats st = (chunk0 + a.chunk <= a.n) ? warp_merge_equal(acc.stats()) : warp_merge(acc.stats());
     if (lane == 0) s.stats[warp] = st;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -81,7 +82,8 @@ __global__ void __launch_bounds__(256) stats_partials_kernel(const double* __res
         else if (wscalar != 1.0) v = v / wscalar;
         acc.add(v);
     }
-    Stats st = warp_merge(acc.stats());
+    // full chunk: equal counts in every lane -> the division-free butterfly (same bits, common.cuh)
+    Stats st = (chunk0 + chunk <= n) ? warp_merge_equal(acc.stats()) : warp_merge(acc.stats());
     if (lane == 0) s_stats[warp] = st;
     __syncthreads();
     if (threadIdx.x == 0) {

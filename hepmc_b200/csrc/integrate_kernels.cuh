@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(256, 1) vegas_sample_kernel(const __grid_const
     __syncthreads();
     block_hist_flush(s.hist, ndim, K, nw, a.hist_partials + (size_t)blockIdx.x * ndim * K);
     // per-thread -> warp -> block (fixed order)
-    Stats st = warp_merge(acc.stats());
+    // full chunk: equal counts in every lane -> the division-free butterfly (same bits, common.cuh)
+    Stats st = (chunk0 + a.chunk <= a.n) ? warp_merge_equal(acc.stats()) : warp_merge(acc.stats());
     if (lane == 0) s.stats[warp] = st;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -387,7 +388,8 @@ __global__ void __launch_bounds__(256) plain_sample_kernel(const __grid_constant
         }
     }
     if constexpr (!fused) return;
-    Stats st = warp_merge(acc.stats());
+    // full chunk: equal counts in every lane -> the division-free butterfly (same bits, common.cuh)
+    Stats st = (chunk0 + a.chunk <= a.n) ? warp_merge_equal(acc.stats()) : warp_merge(acc.stats());
     if (lane == 0) s_stats[warp] = st;
     __syncthreads();
     if (threadIdx.x == 0) {

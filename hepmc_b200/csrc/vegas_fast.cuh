@@ -346,35 +346,47 @@ __global__ void __launch_bounds__(256, OUT ? HEPMC_VFAST_OUT_MINBLOCKS : HEPMC_V
     else run(std::false_type{});
 
     if constexpr (!fused) return;
-    __syncthreads();
-    {   // flush: out[d*K + k] = sum over warps, groups (fixed order)
-        double* out_row = a.hist_partials + (size_t)blockIdx.x * NDIM * K;
-        for (int j = threadIdx.x; j < NDIM * K; j += 256) {
-            const int d = j / K, k = j - d * K;
-            double s = 0.0;
-            for (int w = 0; w < nw; ++w)
-#pragma unroll
-                for (int g = 0; g < G::NG; ++g) s += s_hist[((size_t)w * RW + k) * 32 + g * NDIM + d];
-            out_row[j] = s;
-        }
-    }
+    // ---- chunk epilogue.  Statistics first (they need no other warp's data), so ONE barrier serves both the
+    // histogram flush and the block merge; the last thread (idle in the flush when NDIM*K < 256) merges the warps
+    // while the others flush.
     Stats mine;
     mine.n = (double)cnt;
+    // full chunk with a power-of-two count per thread (every default chunk size): a / n is a multiplication by an
+    // exact reciprocal; full chunk: every lane holds the same count -> warp_merge_equal (no divisions, same bits)
+    const bool pow2_full = (chunk0 + a.chunk <= a.n) && (ppt & (ppt - 1)) == 0;
     if (cnt == 0) { mine.mean = 0.0; mine.m2 = 0.0; }
     else {
-        const double am = sa / mine.n;
+        const double am = pow2_full ? sa * __hiloint2double((992 + __clz(ppt)) << 20, 0) : sa / mine.n;   // 2^-log2(ppt)
         mine.mean = shift + am;
         mine.m2 = sb - sa * am;
         if (mine.m2 < 0.0) mine.m2 = 0.0;
     }
-    Stats st = warp_merge(mine);
+    const Stats st = (chunk0 + a.chunk <= a.n) ? warp_merge_equal(mine) : warp_merge(mine);
     if (lane == 0) s_stats[warp] = st;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 255) {
         Stats r{0.0, 0.0, 0.0};
         for (int w = 0; w < nw; ++w) r = merge(r, s_stats[w]);
         double* o = a.stats_partials + (size_t)blockIdx.x * 3;
         o[0] = r.n; o[1] = r.mean; o[2] = r.m2;
+    }
+    {   // flush: out[d*K + k] = sum over warps, groups (fixed order).  Thread j -> (k = j / NDIM, d = j % NDIM): a warp
+        // reads whole histogram rows (no bank conflict beyond the two wavefronts of a 64-bit access); the loads are
+        // independent, the additions keep their order
+        double* out_row = a.hist_partials + (size_t)blockIdx.x * NDIM * K;
+        for (int j = threadIdx.x; j < NDIM * K; j += 256) {
+            const int k = j / NDIM, d = j - k * NDIM;
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < nw; ++w) {
+                double v[G::NG];
+#pragma unroll
+                for (int g = 0; g < G::NG; ++g) v[g] = s_hist[((size_t)w * RW + k) * 32 + g * NDIM + d];
+#pragma unroll
+                for (int g = 0; g < G::NG; ++g) s += v[g];
+            }
+            out_row[d * K + k] = s;
+        }
     }
 }
 
