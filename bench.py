@@ -429,6 +429,33 @@ def other_workloads(H, _lib, torch, fp64_peak, with_cpu, rank=0, world=1):
                                "roofline": {"bound": "hbm", "achieved": 2 * nk * 18 * 8 / t / 1e9, "peak": hbm, "unit": "GB/s",
                                             "frac": 2 * nk * 18 * 8 / t / 1e9 / hbm, "bytes_per_point": 144}}
         del mck
+        # the sample kernels alone (C ABI, CUDA events, 1e8 points per launch): what the whole-call figures above add
+        # on top is the allocation of the returned arrays and the host side of the call
+        import ctypes
+        nkk = 100_000_000
+        chunk = _lib.default_chunk(nkk)
+        ncl = (nkk + chunk - 1) // chunk
+        blk = camel16._block()
+        xk = torch.empty((16, nkk), dtype=torch.float64, device="cuda")
+        fk = torch.empty(nkk, dtype=torch.float64, device="cuda")
+        wk = torch.empty(nkk, dtype=torch.float64, device="cuda")
+        sp = torch.zeros((ncl, 3), dtype=torch.float64, device="cuda")
+        hp = torch.zeros((ncl, 16 * 15), dtype=torch.float64, device="cuda")
+        gk = H.GridVolumes(ndim=16, divisions=15).device_grid()
+        st = _lib.stream_ptr()
+        t = timed(lambda: _lib.call("hepmc_vegas_sample", ctypes.byref(blk), _lib.ptr(gk), 16, 15, nkk, 0, chunk, 1234, 7,
+                                    H.rng.mode_code(), None, None, _lib.ptr(xk), _lib.ptr(fk), _lib.ptr(wk), None,
+                                    _lib.ptr(sp), _lib.ptr(hp), st))
+        out["vegas16_keep"]["kernel_roofline"] = {"bound": "hbm", "achieved": nkk * 18 * 8 / t / 1e9, "peak": hbm, "unit": "GB/s",
+                                                  "frac": nkk * 18 * 8 / t / 1e9 / hbm, "points_per_s": nkk / t,
+                                                  "what": "hepmc_vegas_sample with x, f, w outputs, 1e8 points per launch"}
+        xr = xk.view(-1)[:nkk * 16]
+        t = timed(lambda: _lib.call("hepmc_plain_mc_sample", ctypes.byref(blk), nkk, 0, chunk, 1234, 7, H.rng.mode_code(), None,
+                                    _lib.ptr(xr), _lib.ptr(fk), _lib.ptr(sp), st))
+        out["plain16_keep"]["kernel_roofline"] = {"bound": "hbm", "achieved": nkk * 17 * 8 / t / 1e9, "peak": hbm, "unit": "GB/s",
+                                                  "frac": nkk * 17 * 8 / t / 1e9 / hbm, "points_per_s": nkk / t,
+                                                  "what": "hepmc_plain_mc_sample with data and f outputs, 1e8 points per launch"}
+        del xk, fk, wk, sp, hp, xr
     # C2: RAMBO 2->4, sqrt(s) = 100 GeV.  BASELINE.json configs[1]: 1e9 points sharded over 8 GPUs (16 GB of output
     # per GPU); on fewer GPUs 2^27 points per launch whole job (16 GiB; larger than L2 at every N)
     m = H.phase_space.Rambo(100., 4)

@@ -300,6 +300,7 @@ static int fill_chain_args(ChainArgs& a, const char* who, int ndim, const double
     a.x0 = x0_dev; a.n_chains = n_chains; a.first_chain = first_chain; a.T = sample_size; a.thin = thin;
     a.n_kept = (sample_size + thin - 1) / thin;
     a.seed = seed; a.stream_id = stream_id; a.z_replay = z; a.u_replay = u;
+    a.keys = philox_expand(seed);
     a.chain = chain_dev; a.last = last_dev; a.accepted = accepted_dev;
     a.total_accepted = reinterpret_cast<unsigned long long*>(total_dev);
     for (int d = 0; d < HEPMC_MAX_CHAIN_DIM; ++d) a.scale[d] = 0.0;
@@ -342,6 +343,14 @@ int hepmc_rwm_chains(const hepmc_density_t* dens, const double* x0_dev, int prop
     const int threads = 128;
     const unsigned blocks = (unsigned)((n_chains + threads - 1) / threads);
     cudaStream_t st = as_stream(stream);
+    // native draws + Gaussian random walk: the kind-specialised throughput kernel (same chains).  The choice depends
+    // on the call's mode only, never on the ensemble size or its sharding.
+    if (proposal_kind == 0 && z_replay_dev == nullptr && u_replay_dev == nullptr) {
+        if (launch_rwm_fast(*dens, a, blocks, st) != -100) {
+            HEPMC_LAUNCH_CHECK();
+            return 0;
+        }
+    }
 #define RWM_CASE(ND) rwm_kernel<ND><<<blocks, threads, 0, st>>>(*dens, a)
     HEPMC_DISPATCH_NDIM(dens->ndim, RWM_CASE);
 #undef RWM_CASE

@@ -12,6 +12,7 @@ struct ChainArgs {
     int64_t n_chains, first_chain, T, thin, n_kept;
     uint64_t seed;
     uint32_t stream_id;
+    PhiloxKey keys;          // round keys of `seed`, expanded on the host: constant-bank operands (chains_rwm_fast.cu)
     const double* z_replay;  // rwm: normals (C, T-1, nd); hmc: momenta (C, T-1, nd)
     const double* u_replay;  // (C, T-1)
     double* chain;           // (C, n_kept, nd) or NULL
@@ -130,6 +131,9 @@ inline bool use_coop(int coop, bool has_elm, int64_t n_chains, int nodes) {
     if (coop >= 0) return coop != 0;
     return n_chains <= coop_max_chains(nodes);
 }
+
+// throughput instance of the random-walk Metropolis kernel (chains_rwm_fast.cu); -100 = no instance
+int launch_rwm_fast(const Dens& dens, const ChainArgs& a, unsigned blocks, cudaStream_t st);
 
 // tensor-core launchers (elm_tc.cu)
 int launch_hmc_tc(const Dens& dens, const Dens& pdist, const hepmc_elm_t& elm, const ChainArgs& a, bool fma_g2,
