@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(128) rwm_kernel(const __grid_constant__ Dens d
     const TabExp texp{tabs};
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = c < a.n_chains;
-    const PhiloxKey key = philox_expand(a.seed);
+    const PhiloxKey& key = a.keys;
     constexpr int NCALL = (NDIM + 1) / 2;  // Philox calls for the proposal normals
     constexpr uint32_t CPS = NCALL + 1;    // + one for the accept uniform
     int64_t acc = 0;

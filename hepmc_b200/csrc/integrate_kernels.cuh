@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256, 1) vegas_sample_kernel(const __grid_const
     double* wf_w = s.wf + warp * 32 * kMaxPPI;
     uint32_t* bins_w = s.bins + warp * 32 * kBinWords * kMaxPPI;
 
-    const PhiloxKey key = philox_expand(a.seed);
+    const PhiloxKey& key = a.keys;   // expanded on the host: constant-bank operands of the rounds
     const bool replay = a.u_replay != nullptr;
     const bool w32 = a.rng_mode != HEPMC_RNG_U52_R10;
     const int per = w32 ? 4 : 2;                       // axes served by one Philox call
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256) plain_sample_kernel(const __grid_constant
     const int ndim = NDIM_T ? NDIM_T : a.ndim;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr bool fused = KIND != HEPMC_NONE;
-    const PhiloxKey key = philox_expand(a.seed);
+    const PhiloxKey& key = a.keys;   // expanded on the host: constant-bank operands of the rounds
     const bool replay = !FAST && a.u_replay != nullptr;
     const int mode = FAST ? RNG : a.rng_mode;
     const bool w32 = mode != HEPMC_RNG_U52_R10;
