@@ -61,13 +61,12 @@ __host__ __device__ inline int vegas_fast_rows(int K) { return K <= 16 ? 16 : K;
 __host__ __device__ inline size_t vegas_fast_smem_bytes(int ndim, int K, int threads) {
     const int nw = threads / 32;
     const int nq = (ndim + 3) / 4;
-    size_t b = (size_t)ndim * vegas_fast_ks(K) * 16;   // grid (bound, size) pairs
+    size_t b = 64 * 8;                                 // 2^(j/T) table of the exponentials (up to 64 entries), first
+    b += (size_t)ndim * vegas_fast_ks(K) * 16;         // grid (bound, size) pairs / rows
     b += 8 * sizeof(Stats);                            // block merge scratch
     b += (size_t)nw * vegas_fast_rows(K) * 32 * 8;   // private histogram columns
     b += (size_t)nw * 32 * 8;                          // f*w tile
     b += (size_t)nw * nq * 36 * 4;                     // packed-bins tile
-    b = (b + 127) & ~(size_t)127;                      // 128-byte aligned: one bank row for the 16-entry table
-    b += 64 * 8;                                       // 2^(j/T) table of the exponentials (up to 64 entries)
     return (b + 15) & ~(size_t)15;
 }
 
@@ -126,7 +125,7 @@ __device__ __forceinline__ bool exp_tab_ok(double x) { return (__double2hiint(x)
 template <int KIND, int NDIM, int RNG, bool OUT, int KP>
 __global__ void __launch_bounds__(256, OUT ? HEPMC_VFAST_OUT_MINBLOCKS : HEPMC_VFAST_MINBLOCKS) vegas_fast_kernel(const __grid_constant__ Dens dens,
                                                                                const __grid_constant__ SampleArgs a) {
-    extern __shared__ __align__(16) double smem_raw[];
+    extern __shared__ __align__(128) double smem_raw[];
     using G = HistGeom<NDIM>;
     constexpr bool fused = KIND != HEPMC_NONE;
     constexpr bool camel = KIND == HEPMC_CAMEL || KIND == HEPMC_UCAMEL;
@@ -139,12 +138,14 @@ __global__ void __launch_bounds__(256, OUT ? HEPMC_VFAST_OUT_MINBLOCKS : HEPMC_V
     const int warp = threadIdx.x >> 5;
     constexpr int nw = 8;
 
-    double2* s_grid2 = reinterpret_cast<double2*>(smem_raw);                       // [NDIM][KS]
+    // the exponential's table first (fixed offset: the look-ups stay LDS -- an address rounded up through an integer
+    // cast made the compiler emit generic LD.E at 4.9 wavefronts per look-up), then the grid rows (128-byte aligned)
+    double* s_exp = smem_raw;                                                      // [kExpTab]
+    double2* s_grid2 = reinterpret_cast<double2*>(smem_raw + kExpTab);             // [NDIM][KS]
     Stats* s_stats = reinterpret_cast<Stats*>(s_grid2 + (size_t)NDIM * KS);
     double* s_hist = reinterpret_cast<double*>(s_stats + 8);                       // [nw][RW][32]
     double* s_wf = s_hist + (size_t)nw * RW * 32;                           // [nw][32]
     uint32_t* s_bins = reinterpret_cast<uint32_t*>(s_wf + nw * 32);                // [nw][NQ][36]
-    double* s_exp = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_bins + nw * NQ * G::ROW) + 127) & ~(uintptr_t)127);
     constexpr bool TABEXP = HEPMC_VFAST_TABEXP && (camel || KIND == HEPMC_BANANA || KIND == HEPMC_GAUSSIAN);
     if constexpr (TABEXP) {
         if (threadIdx.x < kExpTab) s_exp[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / kExpTab));
