@@ -257,6 +257,15 @@ def run_b200(args):
         cpu = {"value": v, "unit": "points/s", "cores": 1, "kind": "port",
                "sample": "2 iterations x 1e6 points of the NumPy port of VegasMC(16,15)(Camel(16)) "
                          "(oracle/hepmc_oracle.py), single process, %.1f s" % cdt}
+    wf = _ncu_wavefronts()
+    clk = sampler.summary()
+    smem_view = None
+    if wf and n_local == N_POINTS and world == 1 and clk.get("sm_mhz"):
+        n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+        peak_w = n_sm * clk["sm_mhz"] * 1e6
+        smem_view = {"bound": "shared-memory data pipe", "unit": "wavefronts/s", "achieved": wf / (kernel_ms * 1e-3),
+                     "peak": peak_w, "frac": wf / (kernel_ms * 1e-3) / peak_w, "wavefronts_per_launch": wf,
+                     "wavefronts_per_point": wf / N_POINTS}
     line = {
         "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -271,7 +280,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": 16, "integral": integral_host},
         # per iteration: vegas_fast_kernel, reduce_slots_kernel, vegas_update_kernel (+ one NCCL all-gather at N > 1)
         "gpu_launches": 3 * steps,
-        "clocks": sampler.summary(),
+        "clocks": clk,
         "roofline": {"bound": "fp64_simt", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, read from the
@@ -290,10 +299,13 @@ def run_b200(args):
                      "hbm_view": {"bound": "hbm", "unit": "GB/s", "peak": peaks.get("hbm_gbs"),
                                   "achieved": nc * (3 + NDIM * DIVISIONS) * 8 / (kernel_ms * 1e-3) / 1e9,
                                   "bytes_per_launch": nc * (3 + NDIM * DIVISIONS) * 8},
-                     "note": "577 thread-instructions per point (round 1: 897), 165 of them FP64; FP64 pipe 36 %, issue "
-                             "slots 66 %, and the shared-memory data pipe 73 % busy (161 wavefronts per 32 points: grid "
-                             "look-ups and the histogram read-modify-writes) -- the binding resource (ncu, profiles/"
-                             "r02_vegas_fast_kernel_ncu_summary.txt)"},
+                     # the binding resource: one 128-byte shared-memory wavefront per cycle and SM is the hardware rate;
+                     # wavefronts per launch from the committed ncu capture (source page), SM clock sampled during the run
+                     "smem_view": smem_view,
+                     "note": "535 thread-instructions per point (round 1: 897), 134 of them FP64; issue slots 64 %, FP64 pipe "
+                             "32 %; 168 shared-memory wavefronts per 32 points (64 grid look-ups, 64 histogram read-modify-"
+                             "writes, 30 staging, 10 exponential-table look-ups; every access at its ideal count) -- the "
+                             "shared-memory data pipe is the binding resource (ncu, profiles/" + NCU_SUMMARY + ")"},
         "cpu_baseline": cpu,
         "others": others,
     }
@@ -314,10 +326,24 @@ def _emit(line):
         os.write(_REAL_STDOUT, text.encode())
 
 
+NCU_SUMMARY = "r02b_vegas_fast_kernel_ncu_summary.txt"
+
+
+def _ncu_wavefronts():
+    """Shared-memory wavefronts of one launch of the headline kernel (sum of `L1 Wavefronts Shared` over the source page
+    of the committed ncu capture, 1e9 points)."""
+    try:
+        txt = open(os.path.join(ROOT, "profiles", NCU_SUMMARY)).read()
+        line = [l for l in txt.splitlines() if l.startswith("shared-memory wavefronts per launch")][0]
+        return float(line.split(":")[1].split()[0])
+    except Exception:
+        return None
+
+
 def _ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the headline kernel from the committed ncu summary."""
     try:
-        txt = open(os.path.join(ROOT, "profiles", "r02_vegas_fast_kernel_ncu_summary.txt")).read()
+        txt = open(os.path.join(ROOT, "profiles", NCU_SUMMARY)).read()
         tot = 0.0
         for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             line = [l for l in txt.splitlines() if key in l][0].split()
@@ -454,7 +480,9 @@ def other_workloads(H, _lib, torch, fp64_peak, with_cpu, rank=0, world=1):
                                     _lib.ptr(xr), _lib.ptr(fk), _lib.ptr(sp), st))
         out["plain16_keep"]["kernel_roofline"] = {"bound": "hbm", "achieved": nkk * 17 * 8 / t / 1e9, "peak": hbm, "unit": "GB/s",
                                                   "frac": nkk * 17 * 8 / t / 1e9 / hbm, "points_per_s": nkk / t,
-                                                  "what": "hepmc_plain_mc_sample with data and f outputs, 1e8 points per launch"}
+                                                  "what": "hepmc_plain_mc_sample with data and f outputs, 1e8 points per launch",
+                                                  "note": "the peak is the measured COPY bandwidth (a read and a write stream); "
+                                                          "a write-only stream can exceed it"}
         del xk, fk, wk, sp, hp, xr
     # C2: RAMBO 2->4, sqrt(s) = 100 GeV.  BASELINE.json configs[1]: 1e9 points sharded over 8 GPUs (16 GB of output
     # per GPU); on fewer GPUs 2^27 points per launch whole job (16 GiB; larger than L2 at every N)

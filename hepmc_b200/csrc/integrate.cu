@@ -236,8 +236,19 @@ __global__ void __launch_bounds__(kRedCols * kRedLanes) reduce_slots_kernel(
         const int cx = threadIdx.x % kRedCols, ry = threadIdx.x / kRedCols;
         const int col = blockIdx.x * kRedCols + cx;
         double acc = 0.0;
-        if (col < ncols)
-            for (int64_t r = r0 + ry; r < r1; r += kRedLanes) acc += hist_rows[r * ncols + col];
+        if (col < ncols) {
+            // eight rows in flight per step, added in row order (one dependent L2 round trip per ROW made this loop
+            // the longest part of the reduction: ~15 rows per lane at 1e9 points on 8 GPUs)
+            int64_t r = r0 + ry;
+            for (; r + 7 * kRedLanes < r1; r += 8 * kRedLanes) {
+                double v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __ldcg(hist_rows + (r + (int64_t)i * kRedLanes) * ncols + col);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc += v[i];
+            }
+            for (; r < r1; r += kRedLanes) acc += __ldcg(hist_rows + r * ncols + col);
+        }
         part[ry][cx] = acc;
         __syncthreads();
 #pragma unroll
@@ -335,7 +346,17 @@ __global__ void __launch_bounds__(256) vegas_update_kernel(const double* __restr
     for (int q = threadIdx.x; q < ndim * K; q += blockDim.x) {
         const int d = q / K, k = q % K;
         double h = 0.0;
-        for (int s = 0; s < n_slots; ++s) h += __ldcg(slot_hist + (size_t)s * hist_stride + q);
+        {   // slot order; the loads of eight slots are independent (a dependent L2 round trip per slot cost ~5 us)
+            int s = 0;
+            for (; s + 8 <= n_slots; s += 8) {
+                double v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __ldcg(slot_hist + (size_t)(s + i) * hist_stride + q);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) h += v[i];
+            }
+            for (; s < n_slots; ++s) h += __ldcg(slot_hist + (size_t)s * hist_stride + q);
+        }
         const double estimate = h / n;                       // vegas.py:108-109
         const double size = grid[d * stride + K + 1 + k];
         const double old_v = est / size;                     // vegas.py:113

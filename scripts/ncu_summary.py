@@ -28,13 +28,20 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]
 si, ii, wi = h.index('Source'), h.index('Instructions Executed'), h.index('# Samples')
+swi = h.index('L1 Wavefronts Shared') if 'L1 Wavefronts Shared' in h else None
+swx = h.index('L1 Wavefronts Shared Excessive') if 'L1 Wavefronts Shared Excessive' in h else None
+smem_w = smem_x = 0
 data = []
 for r in rows[2:]:
     if len(r) < 10 or r[0] in ('Kernel Name', 'Address'):
         if len(data) > 50: break
         continue
     data.append((r[si].strip(), int(r[ii]), int(r[wi])))
+    if swi is not None and r[swi].isdigit():
+        smem_w += int(r[swi]); smem_x += int(r[swx]) if (swx is not None and r[swx].isdigit()) else 0
 tot = sum(d[1] for d in data); samp = sum(d[2] for d in data)
+if smem_w:
+    print("shared-memory wavefronts per launch: %d (excessive: %d)" % (smem_w, smem_x) + ("  per unit: %.3f" % (smem_w / units) if units else ""))
 opc = collections.Counter(); ops = collections.Counter()
 for s, i, w in data:
     t = s.split()

@@ -10,7 +10,8 @@ n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10 ** 9
 ndim, K = 16, 15
 cols = ndim * K
 chunk = _lib.default_chunk(n)
-first, n_local, begins = parallel.local_span(n, chunk)
+ws_emul = int(sys.argv[2]) if len(sys.argv) > 2 else 1     # shape of rank 0 of a ws_emul-GPU run, on one GPU
+first, n_local, begins = parallel.local_span(n, chunk, 0, ws_emul) if ws_emul > 1 else parallel.local_span(n, chunk)
 nslots = len(begins) - 1
 nc = begins[-1]
 dev = torch.device("cuda")

@@ -221,6 +221,26 @@ def test_vegas_statistics_and_determinism():
         H.VegasMC(2, 4)(H.densities.Camel(2), 100, 1, chi=True)   # vegas.py:90-91
 
 
+def test_full_chunk_merge_is_bit_identical_to_the_general_merge():
+    """A full chunk merges its lanes with warp_merge_equal (no divisions: equal counts make the Chan weights 1/2);
+    the same values presented as a PARTIAL chunk of twice the size keep their thread mapping (value i -> thread
+    i mod 256) and take the general warp_merge.  Both rows must agree bit for bit."""
+    dev = torch.device("cuda")
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    for chunk in (2048, 8192, 32768):
+        v = torch.exp(3.0 * torch.randn(chunk, dtype=torch.float64, device=dev, generator=gen)) + 1.0e3
+        rows = []
+        for c in (chunk, 2 * chunk):
+            out = torch.zeros((1, 3), dtype=torch.float64, device=dev)
+            _lib.call("hepmc_stats_partials", _lib.ptr(v), None, 1.0, chunk, c, _lib.ptr(out), _lib.stream_ptr())
+            rows.append(out.cpu().numpy())
+        assert np.array_equal(rows[0], rows[1]), (chunk, rows)
+        ref = v.cpu().numpy()
+        assert rows[0][0, 0] == chunk
+        assert_close(rows[0][0, 1], ref.mean(), 1e-13)
+        assert_close(rows[0][0, 2], ref.var() * chunk, 1e-11)
+
+
 def test_vegas_gpu_count_invariance_at_abi_level():
     """One VEGAS iteration done as 1, 2, 4 and 8 'ranks' (sequentially on one GPU): the
     slot partials and the adapted grid must be BIT-identical."""
