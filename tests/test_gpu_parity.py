@@ -576,6 +576,52 @@ def test_metropolis_native_matches_oracle_draws():
     assert_close(s.data, chain, 1e-10, atol=1e-10)
 
 
+@pytest.mark.parametrize("kind,ndim", [("camel", 1), ("camel", 3), ("camel", 8), ("ucamel", 5), ("gauss", 4),
+                                       ("gauss", 16), ("banana", 3), ("banana", 7)])
+def test_metropolis_throughput_kernel_all_kinds_match_oracle_draws(kind, ndim):
+    """rwm_fast_kernel (native draws + Gaussian random walk) for every density kind it is instantiated for and odd /
+    even / maximal dimensionality: same chains and acceptance counts as the oracle fed with the same Philox draws
+    (per step NCALL = ceil(ndim / 2) calls for the normals, counter stride NCALL + 1, accept uniform from the spare
+    bits of the first call)."""
+    H.seed(99)
+    C, T = 48, 120
+    rs = np.random.RandomState(3)
+    if kind == "banana":
+        dens, pdf = H.densities.Banana(ndim), O.banana_pdf
+        x0 = np.concatenate([np.zeros((C, 1)), np.full((C, 1), 10.0), np.zeros((C, ndim - 2))], axis=1)
+        scale = np.full(ndim, 1.5)
+    elif kind == "gauss":
+        mu, cov = rs.uniform(-1, 1, ndim), rs.uniform(0.5, 2.0, ndim)
+        dens, pdf = H.densities.Gaussian(ndim, mu=mu, cov=cov), (lambda xs: O.gaussian_pdf(xs, mu, cov))
+        x0 = np.tile(mu, (C, 1)) + 0.1
+        scale = np.full(ndim, 0.7)
+    else:
+        bounded = kind == "camel"
+        dens = H.densities.Camel(ndim) if bounded else H.densities.UnconstrainedCamel(ndim)
+        pdf = lambda xs: O.camel_pdf(xs, bounded=bounded)
+        x0 = np.full((C, ndim), 1 / 3) + 0.01 * rs.standard_normal((C, ndim))
+        scale = np.full(ndim, 0.05)
+    met = H.DefaultMetropolis(ndim, dens, H.proposals.Gaussian(ndim, cov=np.diag(scale ** 2)))
+    s = met.sample(T, x0, first_chain=7)
+    ncall = (ndim + 1) // 2
+    cps = ncall + 1
+    w = O.philox_words(99, 0, 7 + np.arange(C), cps * (T - 1)).astype(np.uint32)
+    z = np.empty((C, T - 1, ndim))
+    u = np.empty((C, T - 1))
+    for t in range(T - 1):
+        for k in range(ncall):
+            wk = w[:, cps * t + k]
+            z0, z1 = O.box_muller(O.u52(wk[:, 0], wk[:, 1]), O.u52(wk[:, 2], wk[:, 3]))
+            z[:, t, 2 * k] = z0
+            if 2 * k + 1 < ndim:
+                z[:, t, 2 * k + 1] = z1
+        u[:, t] = O.u24_spare(w[:, cps * t, 0], w[:, cps * t, 2])
+    chain, acc = O.metropolis_chains(pdf, x0, z, u, scale)
+    assert np.array_equal(s.accepted, acc)
+    assert 0 < acc.sum() < C * (T - 1)
+    assert_close(s.data, chain, 1e-10, atol=1e-10)
+
+
 def test_metropolis_options_and_default_proposal():
     H.seed(5)
     met = H.DefaultMetropolis(2, H.densities.Banana(2), H.proposals.Gaussian(2, cov=10 * np.eye(2)))
