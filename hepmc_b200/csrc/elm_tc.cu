@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) elm_grad_tc_kernel(const __grid_
     const uint32_t gbars = u.bars + 8 * N_BARS * grp;
     const uint32_t gtmem = u.tmem_base + GROUP_COLS * grp;
     const int64_t tile0 = (int64_t)blockIdx.x * N_GROUPS + grp, tile_step = (int64_t)gridDim.x * N_GROUPS;
-    const int dbg = g_tc_debug;
+    const int dbg = HEPMC_TC_DBG();
     if (warp < MMA_WARP) {
         ComputeState st;
         const uint32_t lane_base = gtmem + ((uint32_t)((warp & 3) * 32) << 16);
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) hmc_tc_kernel(const __grid_const
     const uint32_t gbars = u.bars + 8 * N_BARS * grp;
     const uint32_t gtmem = u.tmem_base + GROUP_COLS * grp;
     int64_t tile0 = (int64_t)blockIdx.x * N_GROUPS + grp, tile_step = (int64_t)gridDim.x * N_GROUPS;
-    const int dbg = g_tc_debug;
+    const int dbg = HEPMC_TC_DBG();
     if ((dbg & 32) && grp == 1) tile0 = n_tiles;   // development knob: group 1 idle
     if (warp < MMA_WARP) {
         ComputeState cs;
@@ -243,8 +243,14 @@ extern "C" int hepmc_tc_trace(long long* buf_dev) {
 }
 #endif
 
+// development builds only (scripts/tc_debug*.py); the product library has no knob: -1
 extern "C" int hepmc_tc_debug(int mode) {
+#ifdef HEPMC_TC_DEBUG
     return (int)cudaMemcpyToSymbol(tc::g_tc_debug, &mode, sizeof(int));
+#else
+    (void)mode;
+    return -1;
+#endif
 }
 
 int launch_elm_grad_tc(const hepmc_elm_t& elm, int ndim, const double* xs, int64_t n, double* out, bool fma_g2,

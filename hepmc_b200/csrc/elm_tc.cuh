@@ -242,7 +242,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // Read ONCE per kernel into a register: every tcgen05 asm statement is a compiler memory barrier,
 // so reading the global inside the issue loops cost a ~200-cycle load per use (measured with
 // the trace below: 110 instead of 55 cycles per issued MMA).
+// The knob exists only in development builds (make EXTRA=-DHEPMC_TC_DEBUG); in the product library it is the
+// constant 0 and every branch on it is compiled out.
+#ifdef HEPMC_TC_DEBUG
 __device__ int g_tc_debug = 0;
+#define HEPMC_TC_DBG() g_tc_debug
+#else
+#define HEPMC_TC_DBG() 0
+#endif
 
 // development trace (make EXTRA=-DHEPMC_TC_TRACE): clock64 stamps of the hand-offs of group 0 of
 // CTA 0; owner thread 0 writes records [0, 4096), the issuer [4096, 8192): (code, tile, clock)

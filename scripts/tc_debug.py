@@ -15,7 +15,7 @@ H.surrogate.attach_surrogate_gradient(tgt, basis, params, 0.0, w)
 upd = H.hamiltonian.HamiltonianUpdate(tgt, H.densities.Gaussian(8), 20, 0.01, precision="tc")
 x0h = torch.full((148 * 128, 8), 1 / 3, device="cuda", dtype=torch.float64)
 for mode in (0, 1, 2, 3, 4, 6, 11, 15):
-    lib.hepmc_tc_debug(mode)
+    assert lib.hepmc_tc_debug(mode) == 0, "build the library with make EXTRA=-DHEPMC_TC_DEBUG"
     upd.sample(2, x0h, store_chain=False); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); upd.sample(11, x0h, store_chain=False); b.record(); torch.cuda.synchronize()

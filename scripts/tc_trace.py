@@ -16,7 +16,7 @@ w = 0.01 * rs.standard_normal(nodes)
 tgt = H.densities.Camel(8)
 H.surrogate.attach_surrogate_gradient(tgt, basis, params, 0.0, w)
 upd = H.hamiltonian.HamiltonianUpdate(tgt, H.densities.Gaussian(8), 20, 0.01, precision="tc")
-lib.hepmc_tc_debug(mode)
+assert lib.hepmc_tc_debug(mode) == 0, "build the library with make EXTRA=-DHEPMC_TC_DEBUG"
 upd.sample(2, x0h, store_chain=False); torch.cuda.synchronize()
 buf = torch.zeros(3 * 8192, dtype=torch.int64, device="cuda")
 lib.hepmc_tc_trace.argtypes = [ctypes.c_void_p]
