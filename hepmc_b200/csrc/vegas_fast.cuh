@@ -38,6 +38,9 @@ namespace hepmc {
 #ifndef HEPMC_VFAST_OUT_MINBLOCKS
 #define HEPMC_VFAST_OUT_MINBLOCKS 3
 #endif
+#ifndef HEPMC_VFAST_STAGGER_NS
+#define HEPMC_VFAST_STAGGER_NS 400   // start offset between the CTAs sharing an SM (0 = none); 200, 400, 1000 measured alike
+#endif
 #ifndef HEPMC_VFAST_TABEXP
 #define HEPMC_VFAST_TABEXP 1   // the integrand's exponentials by a 64-entry table of 2^(j/64) + degree-5 polynomial
 #endif
@@ -200,6 +203,12 @@ __global__ void __launch_bounds__(256, OUT ? HEPMC_VFAST_OUT_MINBLOCKS : HEPMC_V
 
     double shift = 0.0, sa = 0.0, sb = 0.0;
     int cnt = 0;
+    // The three CTAs that share an SM start together and, having equal work, stay in step wave after wave (all in the
+    // Philox stage, then all in the histogram stage).  A start offset of a fraction of a microsecond between them
+    // breaks the lock-step for good: -1.4 % kernel time at 1e9 points, any offset from 200 ns to 3 us measured the
+    // same; per-warp offsets alone did nothing (scripts/vegas_kernel_bench.cu).  Consecutive block indices land on
+    // different SMs, blockIdx % 3 separates the co-resident ones (148 % 3 = 1).  A pure delay: results unchanged.
+    if (HEPMC_VFAST_STAGGER_NS) __nanosleep((blockIdx.x % 3) * HEPMC_VFAST_STAGGER_NS);
 
     auto draw = [&](int64_t li, U4 (&r)[NCALL]) {
         const uint64_t g = (uint64_t)(a.first_index + li);
