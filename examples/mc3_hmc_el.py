@@ -1,6 +1,8 @@
 """(MC)^3 with an extreme-learning-machine surrogate gradient: the reference's
 interfaces/mc3_hmc_el.py recipe on the 4-D camel, one chain and an ensemble."""
 import numpy as np
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # run from anywhere
 import hepmc_b200 as hepmc
 from hepmc_b200 import densities, interfaces
 

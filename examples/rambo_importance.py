@@ -2,6 +2,8 @@
 (the pattern of the reference's examples/rambo.py)."""
 import numpy as np
 import torch
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # run from anywhere
 import hepmc_b200 as hepmc
 from hepmc_b200 import densities, ImportanceMC
 

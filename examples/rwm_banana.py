@@ -1,6 +1,8 @@
 """Random-walk Metropolis on the banana density: one chain like the reference's
 examples/rwm_banana.py, then an ensemble of 100 000 chains in one kernel."""
 import numpy as np
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # run from anywhere
 import hepmc_b200 as hepmc
 from hepmc_b200 import densities, proposals, DefaultMetropolis
 

@@ -1,4 +1,6 @@
 """VEGAS integration of the 16-D camel (BASELINE config C3 at half size: 10 iterations of 5e8 points, ~0.2 s on a B200)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # run from anywhere
 import hepmc_b200 as hepmc
 from hepmc_b200 import densities, VegasMC
 
