@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) mc3_kernel(const __grid_constant__ Dens d
             density_pot_gradient_n<NDIM>(dens, q, grad);
         }
     };
-    const PhiloxKey key = philox_expand(a.seed);
+    const PhiloxKey& key = a.keys;   // expanded on the host: constant-bank operands
     constexpr int NCALL = (NDIM + 1) / 2;
     constexpr uint32_t CPS = NCALL + 2;  // [selector + channel pick | NCALL sample draws | accept uniform]
     int64_t acc = 0, nloc = 0;
@@ -83,6 +83,10 @@ __global__ void __launch_bounds__(128) mc3_kernel(const __grid_constant__ Dens d
 #pragma unroll
         for (int d = 0; d < NDIM; ++d) x[d] = a.x0[c * NDIM + d];
         double pdf = density_pdf_n<NDIM>(dens, x);
+        // mixture density of the CURRENT state (the Hastings ratio needs it at every importance-sampling step): kept
+        // until the state changes instead of being re-evaluated -- the same value, one mixture evaluation less per step
+        double q_x = 0.0;
+        bool q_x_valid = false;
         if (a.chain && writer) store_state<NDIM>(a.chain, c, a.n_kept, 0, x);
         for (int64_t t = 1; t < a.T; ++t) {
             const uint32_t base = (uint32_t)(t - 1) * CPS;
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(128) mc3_kernel(const __grid_constant__ Dens d
                 is_step = u52(r.x, r.y) < m.beta;  // np.random.choice(2, p=[beta, 1-beta]), base.py:170
                 u_ch = u52(r.z, r.w);
             }
-            double cand[NDIM], cpdf, prob;
+            double cand[NDIM], cpdf, prob, q_cand = 0.0;
             nloc += is_step ? 0 : 1;
             if (is_step) {
                 // ---- importance-sampling Metropolis-Hastings: candidate ~ mixture (independent of x)
@@ -132,8 +136,9 @@ __global__ void __launch_bounds__(128) mc3_kernel(const __grid_constant__ Dens d
                     }
                 }
                 cpdf = density_pdf_n<NDIM>(dens, cand);
-                const double q_state = mixture_pdf(s_tab, m.nch, NDIM, x);
-                const double q_cand = mixture_pdf(s_tab, m.nch, NDIM, cand);
+                if (!q_x_valid) { q_x = mixture_pdf(s_tab, m.nch, NDIM, x); q_x_valid = true; }
+                const double q_state = q_x;
+                q_cand = mixture_pdf(s_tab, m.nch, NDIM, cand);
                 prob = cpdf * q_state / pdf / q_cand;  // metropolis.py:46-47 (Hastings ratio)
             } else if (m.local_kind == 0) {
                 // ---- local Gaussian random walk (proposals/gaussian.py:25-27)
@@ -210,6 +215,8 @@ __global__ void __launch_bounds__(128) mc3_kernel(const __grid_constant__ Dens d
                 }
                 pdf = cpdf;
                 acc += changed ? 1 : 0;
+                q_x = q_cand;            // importance-sampling step: known; local step: evaluated when next needed
+                q_x_valid = is_step;
             }
             if (a.chain && writer && (t % a.thin) == 0) store_state<NDIM>(a.chain, c, a.n_kept, t / a.thin, x);
         }
@@ -257,6 +264,7 @@ extern "C" int hepmc_mc3_chains(const hepmc_density_t* dens, const double* chann
     a.x0 = x0_dev; a.n_chains = n_chains; a.first_chain = first_chain; a.T = sample_size; a.thin = thin;
     a.n_kept = (sample_size + thin - 1) / thin;
     a.seed = seed; a.stream_id = stream_id; a.z_replay = draw_replay_dev; a.u_replay = u_replay_dev;
+    a.keys = philox_expand(seed);
     a.chain = chain_dev; a.last = last_dev; a.accepted = accepted_dev;
     a.total_accepted = reinterpret_cast<unsigned long long*>(total_accepted_dev);
     a.step_size = step_size; a.steps = steps;
