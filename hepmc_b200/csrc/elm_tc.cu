@@ -112,7 +112,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) hmc_tc_kernel(const __grid_const
     const TcSetup u = tc_prologue<NDIM, FMA_G2>(smem_tc, elm);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
     const int64_t n_tiles = (a.n_chains + TILE_M - 1) / TILE_M;
-    const int64_t evals_per_tile = (a.T - 1) * (int64_t)(a.steps + 1);
+    // gradient evaluations per tile of chains: one at the start state, then `steps` per transition -- the gradient at a
+    // transition's start state is the last one of the previous trajectory (accepted) or the previous start gradient
+    // (rejected), so it is carried in registers instead of being evaluated again (the reference evaluates steps + 1)
+    // Only in the both-GEMMs instance: the FFMA instance (tc32) has no registers to spare (measured -28 % with the
+    // carried gradient spilled).
+    constexpr bool CARRY = !FMA_G2;
+    const int64_t evals_per_tile = CARRY ? 1 + (a.T - 1) * (int64_t)a.steps : (a.T - 1) * (int64_t)(a.steps + 1);
     const int grp = warp < MMA_WARP ? warp / (N_OWNER / 32) : (warp - MMA_WARP) / N_ISS;
     const int iss_q = warp < MMA_WARP ? 0 : (warp - MMA_WARP) % N_ISS;
     const uint32_t gbars = u.bars + 8 * N_BARS * grp;
@@ -140,6 +146,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) hmc_tc_kernel(const __grid_const
             for (int d = 0; d < NDIM; ++d) x[d] = active ? a.x0[c * NDIM + d] : 0.5;
             double pdf = density_pdf_n<NDIM>(dens, x);
             if (active && a.chain) store_state<NDIM>(a.chain, c, a.n_kept, 0, x);
+            double gx[CARRY ? NDIM : 1];                       // surrogate gradient at the current state x
+            if constexpr (CARRY) compute_eval<NDIM, FMA_G2>(cs, gbars, lane_base, elm.nodes, u.n_node_tiles, dbg, x, gx, u.s.b2);
             for (int64_t t = 1; t < a.T; ++t) {
                 double p0[NDIM], q[NDIM], p[NDIM], grad[NDIM];
                 if (a.z_replay && active) {
@@ -159,7 +167,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) hmc_tc_kernel(const __grid_const
                 }
 #pragma unroll
                 for (int d = 0; d < NDIM; ++d) { q[d] = x[d]; p[d] = p0[d]; }
-                compute_eval<NDIM, FMA_G2>(cs, gbars, lane_base, elm.nodes, u.n_node_tiles, dbg, q, grad, u.s.b2);
+                if constexpr (CARRY) {
+#pragma unroll
+                    for (int d = 0; d < NDIM; ++d) grad[d] = gx[d];
+                } else {
+                    compute_eval<NDIM, FMA_G2>(cs, gbars, lane_base, elm.nodes, u.n_node_tiles, dbg, q, grad, u.s.b2);
+                }
                 for (int s = 0; s < a.steps; ++s) {
 #pragma unroll
                     for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
@@ -188,6 +201,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) hmc_tc_kernel(const __grid_const
                     for (int d = 0; d < NDIM; ++d) {
                         changed = changed || (q[d] != x[d]);
                         x[d] = q[d];
+                        if constexpr (CARRY) gx[d] = grad[d];
                     }
                     pdf = cpdf;
                     acc += changed ? 1 : 0;
