@@ -86,12 +86,12 @@ __device__ __forceinline__ void coop_sum(double (&g)[NDIM], double* red) {
 // steps + 1 gradient evaluations; kin_gradient = Gaussian(mean, diag mass).pot_gradient = (p - mean)/mass
 // (gaussian.py:45-47).  Shared by hmc_kernel, mc3_kernel's local HMC update and leapfrog_kernel
 // (hepmc_leapfrog), so the three run the same arithmetic.
+// `grad` on entry: the gradient at q (the caller has it from the previous trajectory); on exit: the gradient at the
+// final q.  steps evaluations instead of steps + 1.
 template <int NDIM, class GradFn>
-__device__ __forceinline__ void leapfrog_steps(GradFn& gradient, const Dens& pdist, double (&q)[NDIM], double (&p)[NDIM],
-                                               double step_size, int steps) {
+__device__ __forceinline__ void leapfrog_steps_carry(GradFn& gradient, const Dens& pdist, double (&q)[NDIM], double (&p)[NDIM],
+                                                     double (&grad)[NDIM], double step_size, int steps) {
     const double half_eps = step_size / 2;
-    double grad[NDIM];
-    gradient(q, grad);
     for (int s = 0; s < steps; ++s) {
 #pragma unroll
         for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
@@ -101,6 +101,14 @@ __device__ __forceinline__ void leapfrog_steps(GradFn& gradient, const Dens& pdi
 #pragma unroll
         for (int d = 0; d < NDIM; ++d) p[d] -= half_eps * grad[d];
     }
+}
+
+template <int NDIM, class GradFn>
+__device__ __forceinline__ void leapfrog_steps(GradFn& gradient, const Dens& pdist, double (&q)[NDIM], double (&p)[NDIM],
+                                               double step_size, int steps) {
+    double grad[NDIM];
+    gradient(q, grad);
+    leapfrog_steps_carry<NDIM>(gradient, pdist, q, p, grad, step_size, steps);
 }
 
 // Ensembles up to this many chains per call run the cooperative HMC kernel.  Measured crossover of
