@@ -495,7 +495,10 @@ def other_workloads(H, _lib, torch, fp64_peak, with_cpu, rank=0, world=1):
     out["rambo"] = {"metric": "RAMBO 2->4 PS-points/s", "value": nr / t, "points": nr, "rng_mode": H.rng.get_mode(),
                     "roofline": {"bound": "hbm", "achieved": nr * 128 / t / 1e9 / world, "peak": hbm, "unit": "GB/s",
                                  "frac": nr * 128 / t / 1e9 / world / hbm, "bytes_per_point": 128, "per": "GPU",
-                                 "fp64_tflops_algorithmic": 183 * nr / t / 1e12 / world},
+                                 "fp64_tflops_algorithmic": 183 * nr / t / 1e12 / world,
+                                 "note": "ncu (profiles/r02b_rambo_kernel_ncu_summary.txt): 620 thread-instructions per point of "
+                                         "which 284 FP64; FP64 pipe 54 %, issue slots 58 %, DRAM 53 % -- compute bound below the "
+                                         "write roofline, as SURVEY 8(d) expected"},
                     "cpu_baseline": cpu.get("rambo")}
     # C4: banana 2-D RWM: 1e6 chains x 1e4 steps in ONE launch (BASELINE.json configs[3] at full size)
     C, T = 1_000_000, 10_001
@@ -506,7 +509,11 @@ def other_workloads(H, _lib, torch, fp64_peak, with_cpu, rank=0, world=1):
     out["rwm"] = {"metric": "banana-2D RWM chain-steps/s", "value": C * (T - 1) / t, "chains": C, "steps": T - 1,
                   "roofline": {"bound": "fp64_simt", "achieved": 23 * C * (T - 1) / t / 1e12 / world, "peak": fp64_peak,
                                "unit": "TFLOP/s", "frac": 23 * C * (T - 1) / t / 1e12 / world / fp64_peak,
-                               "flop_per_step": 23, "per": "GPU"},
+                               "flop_per_step": 23, "per": "GPU",
+                               "note": "rwm_fast_kernel (ncu, profiles/r02b_rwm_kernels_ncu_summary.txt): 189 thread-instructions "
+                                       "per step of which 72 FP64 (Philox 45, Box-Muller log / sqrt / sincos, the target's exp); "
+                                       "issue slots 67 %, FP64 pipe 51 % busy -- the 23-flop convention counts each "
+                                       "transcendental as one"},
                   "cpu_baseline": cpu.get("rwm")}
     # C5: camel-8D HMC, 1e5 chains x 20 leapfrog, ELM Gaussian-basis surrogate gradient TRAINED by the SURVEY 8(d)
     # recipe: 4000 points (2000 per mode, N(mu, 0.005 I)), values = UnconstrainedCamel(8).pot(xs), random centres
