@@ -289,34 +289,15 @@ __global__ void __launch_bounds__(kRedCols * kRedLanes) reduce_slots_kernel(
     }
 }
 
-// ------------------------------------------------------------------ grid adaptation (one CTA)
-// slot s: statistics at slot_stats + s*stride, histogram at slot_hist + s*stride (stride 3 / ndim*K for
-// separate arrays; 3 + ndim*K for the packed rows of the all-gather buffer)
-__global__ void __launch_bounds__(256) vegas_update_kernel(const double* __restrict__ slot_stats, int64_t stats_stride,
-                                                           const double* __restrict__ slot_hist, int64_t hist_stride,
-                                                           int n_slots, double* __restrict__ grid, int ndim, int K,
-                                                           double c, int j, double* __restrict__ est_var,
-                                                           const unsigned long long* __restrict__ wait_flags,
-                                                           unsigned long long epoch, int* __restrict__ timeout_flag) {
-    extern __shared__ double sm[];
+// Body of the grid adaptation, shared by vegas_update_kernel and the fused small-problem kernel: one CTA of 256
+// threads, `sm` = ndim*K doubles of dynamic shared memory.
+__device__ __forceinline__ void vegas_update_body(const double* __restrict__ slot_stats, int64_t stats_stride,
+                                                  const double* __restrict__ slot_hist, int64_t hist_stride,
+                                                  int n_slots, double* __restrict__ grid, int ndim, int K,
+                                                  double c, int j, double* __restrict__ est_var, double* sm) {
     double* s_new = sm;  // ndim*K new sizes
     __shared__ double s_est, s_n;
     __shared__ Stats s_slot[64];
-    if (wait_flags != nullptr) {
-        // peer-memory exchange: slot s is complete when its flag carries this iteration's epoch.  Bounded spin
-        // (~4 s): a missing peer becomes an error code of the call, never a hung GPU.
-        if ((int)threadIdx.x < n_slots) {
-            const long long t0 = clock64();
-            unsigned long long v = 0;
-            for (;;) {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(wait_flags + threadIdx.x) : "memory");
-                if (v >= epoch) break;
-                if (clock64() - t0 > 8000000000LL) { if (timeout_flag) *timeout_flag = 1 + (int)threadIdx.x; break; }
-                __nanosleep(100);
-            }
-        }
-        __syncthreads();
-    }
     // slot statistics: loaded by n_slots threads at once, merged in slot order by thread 0
     if ((int)threadIdx.x < n_slots && threadIdx.x < 64) {
         const double* ss = slot_stats + (size_t)threadIdx.x * stats_stride;
@@ -366,20 +347,114 @@ __global__ void __launch_bounds__(256) vegas_update_kernel(const double* __restr
         s_new[q] = 1.0 / inv;                                // vegas.py:115
     }
     __syncthreads();
+    // normalisation in three steps so that the K divisions of an axis run in parallel (one thread per axis doing
+    // sum, K divisions and the running sum in one loop was ~5 us of a 10 us kernel at K = 50); same values
+    __shared__ double s_tot[HEPMC_MAX_DIM];
     if (threadIdx.x < ndim) {
         const int d = threadIdx.x;
         double tot = 0.0;
         for (int k = 0; k < K; ++k) tot += s_new[d * K + k];
+        s_tot[d] = tot;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < ndim * K; q += blockDim.x) {
+        const int d = q / K, k = q % K;
+        const double sz = s_new[q] / s_tot[d];               // vegas.py:117
+        s_new[q] = sz;
+        grid[d * stride + K + 1 + k] = sz;
+    }
+    __syncthreads();
+    if (threadIdx.x < ndim) {
+        const int d = threadIdx.x;
         double* gd = grid + d * stride;
         double cum = 0.0;
         gd[0] = 0.0;                                         // App. B2: bounds[d][0] = 0
         for (int k = 0; k < K; ++k) {
-            const double sz = s_new[d * K + k] / tot;        // vegas.py:117
-            gd[K + 1 + k] = sz;
-            cum += sz;                                       // np.cumsum, stratified_volume.py:167
+            cum += s_new[d * K + k];                         // np.cumsum, stratified_volume.py:167
             gd[k + 1] = cum;
         }
     }
+}
+
+// ------------------------------------------------------------------ grid adaptation (one CTA)
+// slot s: statistics at slot_stats + s*stride, histogram at slot_hist + s*stride (stride 3 / ndim*K for
+// separate arrays; 3 + ndim*K for the packed rows of the all-gather buffer)
+__global__ void __launch_bounds__(256) vegas_update_kernel(const double* __restrict__ slot_stats, int64_t stats_stride,
+                                                           const double* __restrict__ slot_hist, int64_t hist_stride,
+                                                           int n_slots, double* __restrict__ grid, int ndim, int K,
+                                                           double c, int j, double* __restrict__ est_var,
+                                                           const unsigned long long* __restrict__ wait_flags,
+                                                           unsigned long long epoch, int* __restrict__ timeout_flag) {
+    extern __shared__ double sm[];
+    if (wait_flags != nullptr) {
+        // peer-memory exchange: slot s is complete when its flag carries this iteration's epoch.  Bounded spin
+        // (~4 s): a missing peer becomes an error code of the call, never a hung GPU.
+        if ((int)threadIdx.x < n_slots) {
+            const long long t0 = clock64();
+            unsigned long long v = 0;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(wait_flags + threadIdx.x) : "memory");
+                if (v >= epoch) break;
+                if (clock64() - t0 > 8000000000LL) { if (timeout_flag) *timeout_flag = 1 + (int)threadIdx.x; break; }
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+    }
+    vegas_update_body(slot_stats, stats_stride, slot_hist, hist_stride, n_slots, grid, ndim, K, c, j, est_var, sm);
+}
+
+// ------------------------------------------------------------------ small problems: reduction + adaptation in one CTA
+// When no slot has more than kSlotGroups rows, every group of the two-level slot reduction holds at most one row: its
+// level-1 result IS that row (merging with empty statistics and adding +0.0 change nothing), and level 2 combines the
+// rows of a slot in group order.  Then one CTA can do the slot reduction and the grid adaptation of a VEGAS iteration
+// with the same values, bit for bit, as reduce_slots_kernel + vegas_update_kernel (test_vegas_small_step_*): one launch
+// of ~6 us instead of two of 14 + 10 us -- at the reference's own sizes (1e5 points per iteration) the iteration is
+// three dependent short kernels and nothing else.
+__global__ void __launch_bounds__(256) vegas_small_step_kernel(const double* __restrict__ stats_rows,
+                                                               const double* __restrict__ hist_rows,
+                                                               const __grid_constant__ RowRanges rr, int ncols,
+                                                               double* __restrict__ packed /* (n_out, 3 + ncols) */,
+                                                               double* __restrict__ grid, int ndim, int K, double c, int j,
+                                                               double* __restrict__ est_var) {
+    extern __shared__ double sm[];
+    const int row = 3 + ncols;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // statistics: lane g holds the row of group g (or empty statistics), merged in warp_merge's fixed butterfly --
+    // what reduce_slots_l2 does with the level-1 results
+    for (int s = warp; s < rr.n_out; s += 8) {
+        const int64_t b = rr.begin[s], len = rr.begin[s + 1] - b;
+        const int64_t r0 = len * lane / kSlotGroups, r1 = len * (lane + 1) / kSlotGroups;
+        Stats u{0.0, 0.0, 0.0};
+        if (r1 > r0) {
+            const double* p = stats_rows + (b + r0) * 3;
+            u = Stats{p[0], p[1], p[2]};
+        }
+        const Stats t = warp_merge(u);
+        if (lane == 0) {
+            double* o = packed + (size_t)s * row;
+            o[0] = t.n; o[1] = t.mean; o[2] = t.m2;
+        }
+    }
+    // histograms: rows of the slot in order
+    for (int idx = threadIdx.x; idx < rr.n_out * ncols; idx += blockDim.x) {
+        const int s = idx / ncols, col = idx - s * ncols;
+        const int64_t b = rr.begin[s], e = rr.begin[s + 1];
+        double acc = 0.0;
+        int64_t r = b;
+        for (; r + 8 <= e; r += 8) {
+            double v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = hist_rows[(r + i) * ncols + col];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc += v[i];
+        }
+        for (; r < e; ++r) acc += hist_rows[r * ncols + col];
+        packed[(size_t)s * row + 3 + col] = acc;
+    }
+    __threadfence();
+    __syncthreads();
+    vegas_update_body(packed, row, packed + 3, row, rr.n_out, grid, ndim, K, c, j, est_var, sm);
 }
 
 // ------------------------------------------------------------------ GridVolumes.pdf
@@ -455,10 +530,14 @@ static int check_sample_common(const char* who, int ndim, int K, int64_t n, int6
         break;
 
 static int max_optin_smem() {
-    int dev = 0, maxs = 0;
+    static int cached_dev = -1, cached = 0;
+    int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&maxs, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    return maxs;
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cached_dev = dev;
+    }
+    return cached;
 }
 
 // fast = native RNG: compile-time (kind, ndim, rng mode) instance when one exists (ndim <= 16), with or
@@ -773,10 +852,25 @@ int hepmc_vegas_integrate(const hepmc_density_t* dens, double* grid_dev, int ndi
     int64_t begin[HEPMC_N_SLOTS + 1];
     slot_ranges(nc, begin);
     HEPMC_CUDA(cudaMemsetAsync(scratch + (size_t)HEPMC_N_SLOTS * kSlotGroups * (3 + cols), 0, 256, as_stream(stream)));
+    // small problems (at most kSlotGroups chunks per slot): reduction and adaptation in one single-CTA launch
+    bool small = true;
+    for (int s = 0; s < HEPMC_N_SLOTS; ++s) small = small && (begin[s + 1] - begin[s] <= kSlotGroups);
+    RowRanges rr;
+    if (small) {
+        int e = fill_ranges(rr, begin, HEPMC_N_SLOTS, "hepmc_vegas_integrate");
+        if (e) return e;
+        HEPMC_CUDA(cudaFuncSetAttribute(vegas_small_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cols * 8)));
+    }
     for (int j = 0; j < iterations; ++j) {
         int e = hepmc_vegas_sample(dens, grid_dev, ndim, divisions, n, 0, chunk, seed, stream_id0 + (uint32_t)j, rng_mode,
                                    nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats_p, hist_p, stream);
         if (e) return e;
+        if (small) {
+            vegas_small_step_kernel<<<1, 256, (size_t)cols * 8, as_stream(stream)>>>(stats_p, hist_p, rr, (int)cols, packed, grid_dev,
+                                                                                   ndim, divisions, c, j, est_var_dev);
+            HEPMC_LAUNCH_CHECK();
+            continue;
+        }
         e = hepmc_reduce_slots(stats_p, hist_p, begin, HEPMC_N_SLOTS, (int)cols, packed, scratch, stream);
         if (e) return e;
         e = hepmc_vegas_update_grid_packed(packed, HEPMC_N_SLOTS, grid_dev, ndim, divisions, c, j, est_var_dev, stream);

@@ -427,12 +427,22 @@ int launch_fast_none(bool vegas, bool out, int, const Dens&, const SampleArgs&, 
         }                                                                                                   \
         return 0;                                                                                           \
     }
+// the two function attributes are set once per instance (and again only if a call needs more shared memory): at the
+// reference's own problem sizes the host side of a launch is a visible part of the iteration
 #define HEPMC_VFAST_GO(KIND, ND, OUT, RNG, KP)                                                              \
     do {                                                                                                    \
-        HEPMC_CUDA(cudaFuncSetAttribute(vegas_fast_kernel<KIND, ND, RNG, OUT, KP>,                          \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-        HEPMC_CUDA(cudaFuncSetAttribute(vegas_fast_kernel<KIND, ND, RNG, OUT, KP>,                          \
-                                        cudaFuncAttributePreferredSharedMemoryCarveout, 100));              \
+        static size_t smem_set = 0;                                                                         \
+        static int dev_set = -1;                                                                            \
+        int dev_now = 0;                                                                                    \
+        cudaGetDevice(&dev_now);                                                                            \
+        if (smem > smem_set || dev_now != dev_set) {                                                        \
+            HEPMC_CUDA(cudaFuncSetAttribute(vegas_fast_kernel<KIND, ND, RNG, OUT, KP>,                      \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+            HEPMC_CUDA(cudaFuncSetAttribute(vegas_fast_kernel<KIND, ND, RNG, OUT, KP>,                      \
+                                            cudaFuncAttributePreferredSharedMemoryCarveout, 100));          \
+            smem_set = smem;                                                                                \
+            dev_set = dev_now;                                                                              \
+        }                                                                                                   \
         vegas_fast_kernel<KIND, ND, RNG, OUT, KP><<<blocks, 256, smem, st>>>(dens, a);                      \
     } while (0)
 #define HEPMC_VFAST_KP(KIND, ND, OUT, RNG)                                                                  \

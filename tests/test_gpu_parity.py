@@ -241,6 +241,23 @@ def test_full_chunk_merge_is_bit_identical_to_the_general_merge():
         assert_close(rows[0][0, 2], ref.var() * chunk, 1e-11)
 
 
+@pytest.mark.parametrize("ndim,K,n", [(2, 50, 100000), (2, 50, 300), (16, 15, 20000), (5, 7, 60000), (3, 9, 65536)])
+def test_vegas_small_step_kernel_equals_the_two_launch_path(ndim, K, n):
+    """keep_samples=False on one GPU runs the whole call in one library entry; when no slot has more than 32 chunks
+    it reduces and adapts in ONE single-CTA launch (vegas_small_step_kernel).  keep_samples=True drives the general
+    reduce_slots + update kernels from Python.  Same seed: estimates, variances and the adapted grid agree bit for bit."""
+    H.seed(2024)
+    a = H.VegasMC(ndim, divisions=K)
+    sa = a(H.densities.Camel(ndim), n, 4, keep_samples=False, chi=True)
+    H.seed(2024)
+    b = H.VegasMC(ndim, divisions=K)
+    sb = b(H.densities.Camel(ndim), n, 4, keep_samples=True, chi=True)
+    assert np.array_equal(np.asarray(sa.estimates), np.asarray(sb.estimates))
+    assert np.array_equal(np.asarray(sa.variances), np.asarray(sb.variances))
+    assert sa.integral == sb.integral and sa.integral_err == sb.integral_err
+    assert np.array_equal(np.stack(a.volumes.bounds), np.stack(b.volumes.bounds))
+
+
 def test_vegas_gpu_count_invariance_at_abi_level():
     """One VEGAS iteration done as 1, 2, 4 and 8 'ranks' (sequentially on one GPU): the
     slot partials and the adapted grid must be BIT-identical."""
