@@ -227,7 +227,7 @@ def test_full_chunk_merge_is_bit_identical_to_the_general_merge():
     i mod 256) and take the general warp_merge.  Both rows must agree bit for bit."""
     dev = torch.device("cuda")
     gen = torch.Generator(device="cuda").manual_seed(11)
-    for chunk in (2048, 8192, 32768):
+    for chunk in (2048, 8192, 32768, 768, 2560):      # also counts per thread that are not powers of two
         v = torch.exp(3.0 * torch.randn(chunk, dtype=torch.float64, device=dev, generator=gen)) + 1.0e3
         rows = []
         for c in (chunk, 2 * chunk):
