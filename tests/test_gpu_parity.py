@@ -258,6 +258,41 @@ def test_vegas_small_step_kernel_equals_the_two_launch_path(ndim, K, n):
     assert np.array_equal(np.stack(a.volumes.bounds), np.stack(b.volumes.bounds))
 
 
+@pytest.mark.parametrize("chunk", [2048, 2560, 768])
+def test_vegas_fused_and_two_kernel_partial_rows_at_abi_level(chunk):
+    """Partial rows (count, mean, M2 | histogram) of the fused throughput kernel against the two-kernel path (sample-only
+    instance -> integrand values -> hepmc_vegas_accumulate) for chunk sizes whose per-thread count is and is not a power
+    of two, with a ragged last chunk: bit-identical."""
+    from hepmc_b200.core.integration import engine
+    dev = torch.device("cuda")
+    ndim, K = 5, 9
+    n = 6 * chunk + 333
+    nc = (n + chunk - 1) // chunk
+    grid = H.GridVolumes(ndim=ndim, divisions=K).device_grid().clone()
+    grid[:, 1:K] += 0.01 * torch.sin(torch.arange(1, K, device=dev, dtype=torch.float64))[None, :]   # uneven bins
+    grid[:, K + 1:] = grid[:, 1:K + 1] - grid[:, 0:K]
+    blk = H.densities.Uniform(ndim)._block()
+    sp = torch.zeros((nc, 3), dtype=torch.float64, device=dev)
+    hp = torch.zeros((nc, ndim * K), dtype=torch.float64, device=dev)
+    _lib.call("hepmc_vegas_sample", ctypes.byref(blk), _lib.ptr(grid), ndim, K, n, 0, chunk, 11, 3, H.rng.mode_code(),
+              None, None, None, None, None, None, _lib.ptr(sp), _lib.ptr(hp), _lib.stream_ptr())
+    nb = engine.none_block(ndim)
+    x = torch.empty((ndim, n), dtype=torch.float64, device=dev)
+    w = torch.empty(n, dtype=torch.float64, device=dev)
+    idx = torch.empty((ndim, n), dtype=torch.int64, device=dev)
+    sp0 = torch.zeros((nc, 3), dtype=torch.float64, device=dev)
+    hp0 = torch.zeros((nc, ndim * K), dtype=torch.float64, device=dev)
+    _lib.call("hepmc_vegas_sample", ctypes.byref(nb), _lib.ptr(grid), ndim, K, n, 0, chunk, 11, 3, H.rng.mode_code(),
+              None, None, _lib.ptr(x), None, _lib.ptr(w), _lib.ptr(idx), _lib.ptr(sp0), _lib.ptr(hp0), _lib.stream_ptr())
+    f = torch.ones(n, dtype=torch.float64, device=dev)          # Uniform(ndim).pdf inside the cube
+    sp2 = torch.zeros((nc, 3), dtype=torch.float64, device=dev)
+    hp2 = torch.zeros((nc, ndim * K), dtype=torch.float64, device=dev)
+    _lib.call("hepmc_vegas_accumulate", _lib.ptr(f), _lib.ptr(w), _lib.ptr(idx), ndim, K, n, chunk,
+              _lib.ptr(sp2), _lib.ptr(hp2), _lib.stream_ptr())
+    assert float(sp[:, 0].sum().item()) == n
+    assert torch.equal(sp, sp2) and torch.equal(hp, hp2)
+
+
 def test_vegas_gpu_count_invariance_at_abi_level():
     """One VEGAS iteration done as 1, 2, 4 and 8 'ranks' (sequentially on one GPU): the
     slot partials and the adapted grid must be BIT-identical."""
